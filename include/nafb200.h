@@ -1,0 +1,176 @@
+/*
+ * nafb200.h -- C ABI of libnafb200.so, the B200 (sm_100a) hot path of NAF
+ * (Neural Attenuation Fields: ray sampling -> multi-resolution hash-grid encoding ->
+ * density MLP -> Beer-Lambert line integral -> L2 projection loss -> backward -> Adam,
+ * plus the forward-only full-volume voxel query).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  Every `const float*` etc. is a
+ *     DEVICE pointer unless the parameter name starts with `h_` (host pointer).
+ *   - the caller owns every buffer (outputs and workspaces included); nothing is allocated
+ *     here, nothing is retained after the call returns (kernels are enqueued on `stream`).
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - return value: NAFB_OK (0) or an error code; nafb_last_error() returns the message of
+ *     the last failure on the calling thread (thread-local).  There is no CPU fallback.
+ *   - "reference" citations are file:line under the reference repository
+ *     (holuca/NeuralVolumetricReconstructionForMedicalImages).
+ */
+#ifndef NAFB200_H
+#define NAFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAFB_ABI_VERSION 1
+
+enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
+/* head activation of the density MLP: reference src/network/network.py:23-32 */
+enum nafb_activation { NAFB_ACT_SIGMOID = 0, NAFB_ACT_LRELU = 1, NAFB_ACT_TANH = 2, NAFB_ACT_NONE = 3 };
+/* layout of the encoder output / incoming gradient */
+enum nafb_layout { NAFB_LAYOUT_LBC = 0 /* [L,B,C], reference FFI (hashencoder.cu:96) */,
+                   NAFB_LAYOUT_BLC = 1 /* [B,L*C], what hashgrid.py:40 permutes to   */ };
+
+#define NAFB_MAX_LEVELS 32
+#define NAFB_MAX_LAYERS 8
+
+typedef void *nafb_stream_t;
+
+int nafb_abi_version(void);
+const char *nafb_last_error(void);
+/* SM count / compute capability of the current device (used to size persistent grids). */
+int nafb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------ hash-grid descriptor
+ * Mirrors HashEncoder's state (reference src/encoder/hashencoder/hashgrid.py:77-113):
+ * `h_offsets` are ENTRY offsets per level (L+1 values, host memory), `table` is the
+ * embeddings parameter [h_offsets[L], C]. */
+typedef struct nafb_grid {
+    const float *table;       /* device, [n_entries, C] fp32 */
+    const int32_t *h_offsets; /* HOST, [L+1] */
+    uint32_t D;               /* 2 or 3 */
+    uint32_t C;               /* 1, 2, 4 or 8 */
+    uint32_t L;               /* 1..NAFB_MAX_LEVELS */
+    uint32_t H;               /* base resolution */
+} nafb_grid;
+
+/* Replaces _backend.hash_encode_forward (reference src/encoder/hashencoder/src/bindings.cpp:6,
+ * hashencoder.h:13, hashencoder.cu:373-396).
+ *   inputs  [B, D] in [0,1]; outputs [L,B,C] (layout LBC) or [B,L*C] (layout BLC), overwritten;
+ *   dy_dx   [B, L*D*C] when calc_grad_inputs != 0 (overwritten), else ignored (may be NULL).
+ * Errors: D not in {2,3} or C not in {1,2,4,8} -> NAFB_ERR_UNSUPPORTED with the reference's
+ * message "GridEncoding: C must be 1, 2, 4, or 8." (hashencoder.cu:310,324). */
+int nafb_hash_encode_forward(const nafb_grid *grid, const float *inputs, float *outputs, uint32_t B,
+                             int out_layout, int calc_grad_inputs, float *dy_dx, nafb_stream_t stream);
+
+/* Replaces _backend.hash_encode_backward (bindings.cpp:7, hashencoder.h:14, hashencoder.cu:398-428).
+ *   grad [B, L*C] (layout BLC, what autograd hands over) or [L,B,C];
+ *   grad_table [n_entries, C]: ACCUMULATED into (caller pre-zeroes, hashgrid.py:59);
+ *   grad_inputs [B, D]: accumulated into when calc_grad_inputs != 0 (hashencoder.cu:295). */
+int nafb_hash_encode_backward(const nafb_grid *grid, const float *grad, const float *inputs,
+                              float *grad_table, uint32_t B, int grad_layout, int calc_grad_inputs,
+                              const float *dy_dx, float *grad_inputs, nafb_stream_t stream);
+
+/* One fused pass min/max over a float buffer -> out2[0] = min, out2[1] = max
+ * (the range check of hashgrid.py:122 without two separate reductions). */
+int nafb_minmax(const float *x, uint64_t n, float *out2, nafb_stream_t stream);
+
+/* ------------------------------------------------------------------ density network
+ * Mirrors DensityNetwork (reference src/network/network.py:5-58): encoder -> n_layers Linear,
+ * LeakyReLU(0.01) after every hidden layer, skip layers take cat([encoding, h]), head act. */
+typedef struct nafb_mlp {
+    uint32_t n_layers;                  /* 2..NAFB_MAX_LAYERS (hidden layers + output layer) */
+    uint32_t in_dim;                    /* encoder.output_dim = L*C */
+    uint32_t hidden;                    /* hidden_dim */
+    uint32_t out_dim;                   /* 1 */
+    uint32_t skip_mask;                 /* bit i set <=> layer i takes cat([enc, h]) */
+    uint32_t head;                      /* enum nafb_activation */
+    const float *W[NAFB_MAX_LAYERS];    /* device, nn.Linear weight [out, in] row-major */
+    const float *b[NAFB_MAX_LAYERS];    /* device, [out] */
+} nafb_mlp;
+
+typedef struct nafb_mlp_grads {
+    float *gW[NAFB_MAX_LAYERS]; /* device, same shapes as W; ACCUMULATED into */
+    float *gb[NAFB_MAX_LAYERS];
+} nafb_mlp_grads;
+
+/* Where a kernel takes its sample points from. */
+enum nafb_point_source {
+    NAFB_SRC_POINTS = 0, /* pts [P,3] world coordinates in [-bound, bound]            */
+    NAFB_SRC_RAYS = 1,   /* rays [N,8] + sampling of render.py:88-105, P = N*n_samples */
+    NAFB_SRC_VOXELS = 2  /* voxel lattice of tigre.py:388-400, P = (i1-i0)*n2*n3       */
+};
+
+typedef struct nafb_sampler {
+    /* NAFB_SRC_POINTS */
+    const float *pts;        /* [P,3] */
+    uint64_t n_points;       /* P */
+    /* NAFB_SRC_RAYS: reference src/render/render.py:88-105 */
+    const float *rays;       /* [N,8] = origin(3), direction(3), near, far */
+    const float *t_rand;     /* [N,S] uniforms in [0,1) (torch.rand of render.py:99) or NULL when !perturb */
+    uint32_t n_rays;
+    uint32_t n_samples;
+    int32_t perturb;
+    /* NAFB_SRC_VOXELS: reference src/dataset/tigre.py:388-400 */
+    uint32_t n1, n2, n3;     /* full lattice */
+    uint32_t i0, i1;         /* slab [i0, i1) of the outermost index handled by this call */
+    double s1, s2, s3;       /* half extents sVoxel/2 - dVoxel/2 (float64 linspace end points) */
+    /* common */
+    float bound;             /* net.bound: positions are normalised as (x + bound) * (1/(2 bound)) */
+    float clamp;             /* render.py:104: fp32(bound - 1e-6); RAYS source clamps to +-clamp */
+} nafb_sampler;
+
+/* sigma[P*out_dim] = DensityNetwork.forward(points)   (network.py:34-58; forward only).
+ * With src == NAFB_SRC_RAYS and acc != NULL it also integrates (render.py:192-201):
+ *   acc[r] = sum_i sigma[r,i] * (z[r,i+1]-z[r,i]) * |d_r|   (last delta 1e-10)
+ * and writes z_vals [N,S] / pts [N,S,3] when those pointers are non-NULL.
+ * flags[0] is OR-ed with 1 if a position leaves [-bound, bound] (hashgrid.py:122), 2 on NaN/Inf. */
+int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src,
+                         float *sigma, float *acc, float *z_vals, float *pts_out, int32_t *flags,
+                         nafb_stream_t stream);
+
+/* Backward of the above.  dsigma [P] (src POINTS) or dacc [N] (src RAYS: dsigma is derived as
+ * dacc[r] * delta[r,i] in-kernel).  Recomputes the forward activations (nothing but the
+ * points was saved), accumulates MLP gradients and scatters into grad_table.
+ *   workspace: nafb_density_backward_workspace_bytes() bytes of device scratch. */
+uint64_t nafb_density_backward_workspace_bytes(const nafb_mlp *mlp);
+int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src,
+                          const float *dsigma_or_dacc, float *grad_table, const nafb_mlp_grads *grads,
+                          void *workspace, nafb_stream_t stream);
+
+/* ------------------------------------------------------------------ sampling / integral (unfused API)
+ * nafb_sample_points: render.py:88-105 -> z_vals [N,S], pts [N,S,3]; tv_partial [N] gets
+ * sum_i |pts[r,i+1]-pts[r,i]|_1 per ray (render.py:16-28) when non-NULL. */
+int nafb_sample_points(const nafb_sampler *smp, float *z_vals, float *pts, float *tv_partial,
+                       nafb_stream_t stream);
+/* raw2outputs (render.py:178-212), raw [N,S,out_dim] (channel 0 integrated): acc [N];
+ * absdiff [N,S] = (1e-10, |raw_i - raw_{i-1}|) when non-NULL (the un-normalised `weights`). */
+int nafb_ray_integral_forward(const float *raw, uint32_t out_dim, const float *z_vals, const float *rays,
+                              float *acc, float *absdiff, uint32_t n_rays, uint32_t n_samples,
+                              nafb_stream_t stream);
+/* d raw[r,i,0] = dacc[r] * delta[r,i] (other channels zero). */
+int nafb_ray_integral_backward(const float *dacc, uint32_t out_dim, const float *z_vals, const float *rays,
+                               float *draw, uint32_t n_rays, uint32_t n_samples, nafb_stream_t stream);
+
+/* ------------------------------------------------------------------ loss
+ * Masked, chunk-wise MSE of train.py:69-127 / loss.py:26-46:
+ *   loss = sum_chunks mean_{r in chunk, mask[r]} (target[r]-pred[r])^2 ;  dpred[r] = dloss/dpred[r] * gscale.
+ * mask may be NULL (all rays valid); chunk == 0 means one chunk.  loss_out[0] = loss,
+ * loss_out[1] = number of valid rays.  Single deterministic block. */
+int nafb_mse_loss(const float *pred, const float *target, const uint8_t *mask, uint32_t n, uint32_t chunk,
+                  float gscale, float *loss_out, float *dpred, nafb_stream_t stream);
+
+/* ------------------------------------------------------------------ optimiser
+ * torch.optim.Adam (trainer.py:54: betas (0.9,0.999), eps 1e-8, no weight decay, no amsgrad),
+ * one fused pass over a flat parameter vector; grad is zeroed in the same pass when zero_grad != 0
+ * (trainer.py:138 optimizer.zero_grad()).  `step` is the 1-based step count. */
+int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float lr,
+                   float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad,
+                   nafb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAFB200_H */

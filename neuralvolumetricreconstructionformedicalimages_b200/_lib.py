@@ -1,0 +1,152 @@
+"""ctypes binding of libnafb200.so (C ABI declared in include/nafb200.h).
+
+This is the only place where the package touches native code.  There is NO fallback: if the
+library is missing or cannot be loaded, every operator of the package raises RuntimeError.
+PyTorch is used for device memory and streams only -- kernels receive raw device pointers
+and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnafb200.so")
+
+NAFB_MAX_LEVELS = 32
+NAFB_MAX_LAYERS = 8
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
+ACT = {"sigmoid": 0, "relu": 1, "tanh": 2, "none": 3}
+LAYOUT_LBC, LAYOUT_BLC = 0, 1
+SRC_POINTS, SRC_RAYS, SRC_VOXELS = 0, 1, 2
+
+c_f32p = ctypes.c_void_p
+u32, u64, i32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int32
+
+
+class Grid(ctypes.Structure):
+    _fields_ = [("table", ctypes.c_void_p), ("h_offsets", ctypes.c_void_p), ("D", u32), ("C", u32), ("L", u32), ("H", u32)]
+
+
+class Mlp(ctypes.Structure):
+    _fields_ = [("n_layers", u32), ("in_dim", u32), ("hidden", u32), ("out_dim", u32), ("skip_mask", u32), ("head", u32),
+                ("W", ctypes.c_void_p * NAFB_MAX_LAYERS), ("b", ctypes.c_void_p * NAFB_MAX_LAYERS)]
+
+
+class MlpGrads(ctypes.Structure):
+    _fields_ = [("gW", ctypes.c_void_p * NAFB_MAX_LAYERS), ("gb", ctypes.c_void_p * NAFB_MAX_LAYERS)]
+
+
+class Sampler(ctypes.Structure):
+    _fields_ = [("pts", ctypes.c_void_p), ("n_points", u64), ("rays", ctypes.c_void_p), ("t_rand", ctypes.c_void_p),
+                ("n_rays", u32), ("n_samples", u32), ("perturb", i32),
+                ("n1", u32), ("n2", u32), ("n3", u32), ("i0", u32), ("i1", u32),
+                ("s1", ctypes.c_double), ("s2", ctypes.c_double), ("s3", ctypes.c_double),
+                ("bound", ctypes.c_float), ("clamp", ctypes.c_float)]
+
+
+_SIGNATURES = {
+    "nafb_abi_version": (ctypes.c_int, []),
+    "nafb_last_error": (ctypes.c_char_p, []),
+    "nafb_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
+    "nafb_hash_encode_forward": (ctypes.c_int, [ctypes.POINTER(Grid), c_f32p, c_f32p, u32, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_void_p]),
+    "nafb_hash_encode_backward": (ctypes.c_int, [ctypes.POINTER(Grid), c_f32p, c_f32p, c_f32p, u32, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p, ctypes.c_void_p]),
+    "nafb_minmax": (ctypes.c_int, [c_f32p, u64, c_f32p, ctypes.c_void_p]),
+    "nafb_density_forward": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), ctypes.c_int, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nafb_density_backward_workspace_bytes": (u64, [ctypes.POINTER(Mlp)]),
+    "nafb_density_backward": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), ctypes.c_int, c_f32p, c_f32p, ctypes.POINTER(MlpGrads), ctypes.c_void_p, ctypes.c_void_p]),
+    "nafb_sample_points": (ctypes.c_int, [ctypes.POINTER(Sampler), c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
+    "nafb_ray_integral_forward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
+    "nafb_ray_integral_backward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
+    "nafb_mse_loss": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, u32, u32, ctypes.c_float, c_f32p, c_f32p, ctypes.c_void_p]),
+    "nafb_adam_step": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, u32, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names every build of the library must export (== the declarations of include/nafb200.h)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load libnafb200.so once. Raises RuntimeError when it is absent -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the sm_100a CUDA extension has not been built. Run "
+                "`python -m neuralvolumetricreconstructionformedicalimages_b200.build` (needs nvcc). "
+                "This package has no CPU or eager-PyTorch fallback.")
+        try:
+            L = ctypes.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise RuntimeError(f"could not load {LIB_PATH}: {e}") from e
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.nafb_abi_version() != 1:
+            raise RuntimeError("libnafb200.so ABI version mismatch; rebuild the extension")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, value_error: bool = False):
+    if rc != OK:
+        msg = lib().nafb_last_error().decode()
+        if rc == ERR_UNSUPPORTED and not value_error:
+            raise RuntimeError(msg)
+        raise (ValueError if value_error else RuntimeError)(msg)
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
+    """Same conditions as the reference's CHECK_CUDA / CHECK_CONTIGUOUS / CHECK_IS_* (hashencoder.cu:17-20)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        kind = "an int" if dtype == torch.int32 else "a float32"
+        raise RuntimeError(f"{name} must be {kind} tensor (got {t.dtype})")
+    return t
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def make_grid(table: torch.Tensor, offsets_np: np.ndarray, D: int, C: int, H: int) -> Grid:
+    """offsets_np must stay alive while the returned struct is used (it holds a host pointer)."""
+    assert offsets_np.dtype == np.int32 and offsets_np.flags["C_CONTIGUOUS"]
+    return Grid(table.data_ptr(), offsets_np.ctypes.data, D, C, offsets_np.shape[0] - 1, H)
+
+
+def make_mlp(weights, biases, in_dim, hidden, out_dim, skips, head: str) -> Mlp:
+    n = len(weights)
+    if n > NAFB_MAX_LAYERS:
+        raise RuntimeError(f"num_layers={n} exceeds NAFB_MAX_LAYERS={NAFB_MAX_LAYERS}")
+    m = Mlp()
+    m.n_layers, m.in_dim, m.hidden, m.out_dim = n, in_dim, hidden, out_dim
+    m.skip_mask = sum(1 << int(s) for s in set(skips) if 0 <= int(s) < 32)
+    m.head = ACT[head]
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        m.W[i] = w.data_ptr()
+        m.b[i] = b.data_ptr()
+    return m
+
+
+def make_mlp_grads(gws, gbs) -> MlpGrads:
+    g = MlpGrads()
+    for i, (w, b) in enumerate(zip(gws, gbs)):
+        g.gW[i] = w.data_ptr() if w is not None else None
+        g.gb[i] = b.data_ptr() if b is not None else None
+    return g

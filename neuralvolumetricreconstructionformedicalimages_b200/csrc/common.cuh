@@ -1,0 +1,143 @@
+// common.cuh -- shared device helpers of libnafb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nafb200.h"
+
+// ----------------------------------------------------------------------------- host side
+void nafb_set_error(const char *fmt, ...);
+#define NAFB_FAIL(code, ...)          \
+    do {                              \
+        nafb_set_error(__VA_ARGS__);  \
+        return (code);                \
+    } while (0)
+#define NAFB_CHECK_LAUNCH(name)                                                        \
+    do {                                                                               \
+        cudaError_t e_ = cudaGetLastError();                                           \
+        if (e_ != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+int nafb_sm_count();
+
+// ----------------------------------------------------------------------------- level table
+// Per-level constants of the multi-resolution grid, evaluated once on the host and passed
+// BY VALUE in the kernel parameter block (constant bank: no loads, no runtime `%` for the
+// power-of-two levels).  Restates hashencoder.cu:55-74 and :98-100.
+struct LevelParams {
+    uint32_t offset;   // entry offset of the level                         (hashencoder.cu:94)
+    uint32_t size;     // hashmap_size = offsets[l+1]-offsets[l]            (:98)
+    uint32_t mask;     // size-1 if size is a power of two, else 0 (use `% size`)
+    float scale;       // fma(exp2f(l), H, -1)                              (:99)
+    uint32_t s1, s2;   // uint32-wrapped linear strides (res+1), (res+1)^2  (:61-65)
+    uint32_t hashed;   // 1: xor-prime hash, 0: (wrapped) linear index      (:67-71)
+};
+
+struct GridParams {
+    const float *table;
+    uint32_t L, C, D, H;
+    LevelParams lv[NAFB_MAX_LEVELS];
+};
+
+// Builds GridParams from the ABI descriptor. Returns NAFB_OK or an error (message set).
+int nafb_make_grid_params(const nafb_grid *g, GridParams *out);
+
+// ----------------------------------------------------------------------------- device side
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t wrap_index(uint32_t idx, const LevelParams &lp) {
+    return lp.mask ? (idx & lp.mask) : (idx % lp.size);
+}
+
+// get_grid_index<3,C>(ch=0)/C  (hashencoder.cu:55-74); `linear` already carries the uint32 wrap.
+__device__ __forceinline__ uint32_t grid_entry3(const LevelParams &lp, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t hashed = x ^ (y * 19349663u) ^ (z * 83492791u);   // fast_hash<3>, :36-52
+    const uint32_t linear = x + y * lp.s1 + z * lp.s2;
+    return wrap_index(lp.hashed ? hashed : linear, lp);
+}
+__device__ __forceinline__ uint32_t grid_entry2(const LevelParams &lp, uint32_t x, uint32_t y) {
+    const uint32_t hashed = x ^ (y * 19349663u);
+    const uint32_t linear = x + y * lp.s1;
+    return wrap_index(lp.hashed ? hashed : linear, lp);
+}
+
+// pos = fma(x, scale, 0.5); g = floor(pos); f = pos - g   (hashencoder.cu:106-111).
+__device__ __forceinline__ void locate(float x01, float scale, uint32_t &g, float &f) {
+    const float pos = __fmaf_rn(x01, scale, 0.5f);
+    const float fl = floorf(pos);
+    g = (uint32_t)fl;
+    f = __fsub_rn(pos, (float)g);
+}
+
+// read-only vector loads of C consecutive floats of a table entry
+template <int C> struct EntryVec;
+template <> struct EntryVec<1> { float v[1]; };
+template <> struct EntryVec<2> { float v[2]; };
+template <> struct EntryVec<4> { float v[4]; };
+template <> struct EntryVec<8> { float v[8]; };
+
+template <int C>
+__device__ __forceinline__ void load_entry(const float *__restrict__ base, uint32_t entry, float (&v)[C]) {
+    if constexpr (C == 1) {
+        v[0] = __ldg(base + entry);
+    } else if constexpr (C == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(base) + entry);
+        v[0] = t.x; v[1] = t.y;
+    } else if constexpr (C == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(base) + entry);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        const float4 t0 = __ldg(reinterpret_cast<const float4 *>(base) + 2 * (size_t)entry);
+        const float4 t1 = __ldg(reinterpret_cast<const float4 *>(base) + 2 * (size_t)entry + 1);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
+        v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    }
+}
+
+// no-return vector reduction into the gradient table (red.global.add.v2.f32 on sm_90+)
+__device__ __forceinline__ void red_add_f32x2(float *addr, float a, float b) {
+    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_f32x4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float *addr, float a) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+template <int C>
+__device__ __forceinline__ void red_add_entry(float *base, uint32_t entry, const float (&v)[C]) {
+    float *p = base + (size_t)entry * C;
+    if constexpr (C == 1) red_add_f32(p, v[0]);
+    else if constexpr (C == 2) red_add_f32x2(p, v[0], v[1]);
+    else if constexpr (C == 4) red_add_f32x4(p, v[0], v[1], v[2], v[3]);
+    else { red_add_f32x4(p, v[0], v[1], v[2], v[3]); red_add_f32x4(p + 4, v[4], v[5], v[6], v[7]); }
+}
+
+__device__ __forceinline__ float leaky_relu(float x) { return x > 0.f ? x : 0.01f * x; }
+
+__device__ __forceinline__ float head_activation(float x, uint32_t head) {
+    switch (head) {
+        case NAFB_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+        case NAFB_ACT_LRELU: return leaky_relu(x);
+        case NAFB_ACT_TANH: return tanhf(x);
+        default: return x;
+    }
+}
+// derivative of the head wrt its pre-activation, given pre-activation x and output y
+__device__ __forceinline__ float head_derivative(float x, float y, uint32_t head) {
+    switch (head) {
+        case NAFB_ACT_SIGMOID: return y * (1.0f - y);
+        case NAFB_ACT_LRELU: return x > 0.f ? 1.0f : 0.01f;
+        case NAFB_ACT_TANH: return 1.0f - y * y;
+        default: return 1.0f;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,172 @@
+// render.cu -- the unfused pieces of the renderer at the reference's Python-op granularity:
+// sampling (src/render/render.py:88-105), raw2outputs (:178-212) and the masked chunk-wise
+// MSE of train.py:69-127 / src/loss/loss.py:26-46.  The fused training path does not launch
+// these (it samples and integrates inside the density kernels); they back the drop-in
+// render()/raw2outputs()/calc_mse_loss() operators.
+#include "common.cuh"
+#include "sampler.cuh"
+
+namespace {
+
+// one block per ray: z_vals [N,S], pts [N,S,3], tv_partial[r] = sum_i |pts[r,i+1]-pts[r,i]|_1
+__global__ void __launch_bounds__(128) k_sample_points(const SamplerParams sp, float *__restrict__ z_vals, float *__restrict__ pts,
+                                                       float *__restrict__ tv_partial) {
+    const uint32_t r = blockIdx.x;
+    const uint32_t S = sp.n_samples;
+    const RayRegs R = load_ray(sp.rays, r);
+    const float *tr = sp.t_rand ? sp.t_rand + (size_t)r * S : nullptr;
+    float tv = 0.f;
+    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+        const float z = z_sample(R.near, R.far, i, S, sp.lin_step, sp.perturb != 0, tr);
+        float x[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = ray_point(R.o[d], R.d[d], z, sp.clamp);
+        if (z_vals) z_vals[(size_t)r * S + i] = z;
+        if (pts) {
+            float *q = pts + ((size_t)r * S + i) * 3;
+            q[0] = x[0]; q[1] = x[1]; q[2] = x[2];
+        }
+        if (tv_partial && i + 1 < S) {
+            const float zn = z_sample(R.near, R.far, i + 1, S, sp.lin_step, sp.perturb != 0, tr);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) tv += fabsf(__fsub_rn(ray_point(R.o[d], R.d[d], zn, sp.clamp), x[d]));
+        }
+    }
+    if (tv_partial) {
+        __shared__ float red[4];
+        tv = warp_sum(tv);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tv;
+        __syncthreads();
+        if (threadIdx.x == 0) tv_partial[r] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+}
+
+__device__ __forceinline__ float ray_norm(const float *__restrict__ rays, uint32_t r) {
+    const float dx = __ldg(rays + 8 * (size_t)r + 3), dy = __ldg(rays + 8 * (size_t)r + 4), dz = __ldg(rays + 8 * (size_t)r + 5);
+    return sqrtf(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+}
+
+// one warp per ray: acc[r] = sum_i raw[r,i,0] * (z[i+1]-z[i]) * |d|    (render.py:192-201)
+__global__ void __launch_bounds__(128) k_ray_integral_fwd(const float *__restrict__ raw, uint32_t out_dim, const float *__restrict__ z_vals,
+                                                          const float *__restrict__ rays, float *__restrict__ acc, float *__restrict__ absdiff,
+                                                          uint32_t N, uint32_t S) {
+    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= N) return;
+    const unsigned lane = threadIdx.x & 31;
+    const float norm = ray_norm(rays, r);
+    const float *z = z_vals + (size_t)r * S;
+    const float *rw = raw + (size_t)r * S * out_dim;
+    float s = 0.f;
+    for (uint32_t i = lane; i < S; i += 32) {
+        const float dist = i + 1 < S ? __fsub_rn(z[i + 1], z[i]) : 1e-10f;
+        s = __fmaf_rn(rw[(size_t)i * out_dim], __fmul_rn(dist, norm), s);
+        if (absdiff) absdiff[(size_t)r * S + i] = i == 0 ? 1e-10f : fabsf(__fsub_rn(rw[(size_t)i * out_dim + out_dim - 1], rw[(size_t)(i - 1) * out_dim + out_dim - 1]));
+    }
+    s = warp_sum(s);
+    if (lane == 0) acc[r] = s;
+}
+
+__global__ void __launch_bounds__(256) k_ray_integral_bwd(const float *__restrict__ dacc, uint32_t out_dim, const float *__restrict__ z_vals,
+                                                          const float *__restrict__ rays, float *__restrict__ draw, uint32_t N, uint32_t S) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (uint64_t)N * S) return;
+    const uint32_t r = (uint32_t)(p / S), i = (uint32_t)(p - (uint64_t)r * S);
+    const float dist = i + 1 < S ? __fsub_rn(z_vals[p + 1], z_vals[p]) : 1e-10f;
+    const float g = __fmul_rn(__ldg(dacc + r), __fmul_rn(dist, ray_norm(rays, r)));
+    draw[p * out_dim] = g;
+    for (uint32_t c = 1; c < out_dim; ++c) draw[p * out_dim + c] = 0.f;
+}
+
+// single block, deterministic: loss = sum_chunks mean_{valid in chunk} (target - pred)^2
+__global__ void __launch_bounds__(1024) k_mse_loss(const float *__restrict__ pred, const float *__restrict__ target,
+                                                   const uint8_t *__restrict__ mask, uint32_t n, uint32_t chunk, float gscale,
+                                                   float *__restrict__ loss_out, float *__restrict__ dpred) {
+    __shared__ float s_sum[32];
+    __shared__ float s_cnt[32];
+    __shared__ float s_inv;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float total = 0.f, total_cnt = 0.f;
+    for (uint32_t c0 = 0; c0 < n; c0 += chunk) {
+        const uint32_t c1 = c0 + chunk < n ? c0 + chunk : n;
+        float s = 0.f, cnt = 0.f;
+        for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+            if (!mask || mask[i]) {
+                const float d = __fsub_rn(target[i], pred[i]);
+                s = __fmaf_rn(d, d, s);
+                cnt += 1.f;
+            }
+        }
+        s = warp_sum(s);
+        cnt = warp_sum(cnt);
+        if (lane == 0) { s_sum[warp] = s; s_cnt[warp] = cnt; }
+        __syncthreads();
+        if (warp == 0) {
+            float a = lane < (blockDim.x >> 5) ? s_sum[lane] : 0.f;
+            float b = lane < (blockDim.x >> 5) ? s_cnt[lane] : 0.f;
+            a = warp_sum(a);
+            b = warp_sum(b);
+            if (lane == 0) {
+                // an empty chunk gives mean(empty) = NaN in torch; keep that behaviour
+                total += a / b;
+                total_cnt += b;
+                s_inv = 1.0f / b;
+            }
+        }
+        __syncthreads();
+        if (dpred) {
+            const float inv = s_inv;
+            for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+                const bool m = !mask || mask[i];
+                dpred[i] = m ? gscale * 2.0f * __fsub_rn(pred[i], target[i]) * inv : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { loss_out[0] = total; loss_out[1] = total_cnt; }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nafb_sample_points(const nafb_sampler *smp, float *z_vals, float *pts, float *tv_partial, nafb_stream_t stream) {
+    SamplerParams sp;
+    uint64_t P = 0;
+    int rc = nafb_make_sampler_params(smp, NAFB_SRC_RAYS, &sp, &P);
+    if (rc) return rc;
+    if (P == 0) return NAFB_OK;
+    k_sample_points<<<sp.n_rays, 128, 0, (cudaStream_t)stream>>>(sp, z_vals, pts, tv_partial);
+    NAFB_CHECK_LAUNCH("sample_points");
+    return NAFB_OK;
+}
+
+int nafb_ray_integral_forward(const float *raw, uint32_t out_dim, const float *z_vals, const float *rays, float *acc, float *absdiff,
+                              uint32_t n_rays, uint32_t n_samples, nafb_stream_t stream) {
+    if (!raw || !z_vals || !rays || !acc) NAFB_FAIL(NAFB_ERR_INVALID, "ray_integral_forward: null pointer");
+    if (out_dim < 1 || out_dim > 2) NAFB_FAIL(NAFB_ERR_UNSUPPORTED, "Wrong raw shape");  // render.py:210
+    if (n_rays == 0 || n_samples == 0) return NAFB_OK;
+    k_ray_integral_fwd<<<(n_rays + 3) / 4, 128, 0, (cudaStream_t)stream>>>(raw, out_dim, z_vals, rays, acc, absdiff, n_rays, n_samples);
+    NAFB_CHECK_LAUNCH("ray_integral_forward");
+    return NAFB_OK;
+}
+
+int nafb_ray_integral_backward(const float *dacc, uint32_t out_dim, const float *z_vals, const float *rays, float *draw, uint32_t n_rays,
+                               uint32_t n_samples, nafb_stream_t stream) {
+    if (!dacc || !z_vals || !rays || !draw) NAFB_FAIL(NAFB_ERR_INVALID, "ray_integral_backward: null pointer");
+    if (n_rays == 0 || n_samples == 0) return NAFB_OK;
+    const uint64_t P = (uint64_t)n_rays * n_samples;
+    k_ray_integral_bwd<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dacc, out_dim, z_vals, rays, draw, n_rays, n_samples);
+    NAFB_CHECK_LAUNCH("ray_integral_backward");
+    return NAFB_OK;
+}
+
+int nafb_mse_loss(const float *pred, const float *target, const uint8_t *mask, uint32_t n, uint32_t chunk, float gscale, float *loss_out,
+                  float *dpred, nafb_stream_t stream) {
+    if (!pred || !target || !loss_out) NAFB_FAIL(NAFB_ERR_INVALID, "mse_loss: null pointer");
+    if (chunk == 0 || chunk > n) chunk = n ? n : 1;
+    k_mse_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, target, mask, n, chunk, gscale, loss_out, dpred);
+    NAFB_CHECK_LAUNCH("mse_loss");
+    return NAFB_OK;
+}
+
+}  // extern "C"

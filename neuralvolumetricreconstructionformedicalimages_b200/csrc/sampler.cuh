@@ -1,0 +1,157 @@
+// sampler.cuh -- where sample points come from: a points tensor, rays (+ stratified /
+// perturbed sampling, reference src/render/render.py:88-105) or the voxel lattice
+// (reference src/dataset/tigre.py:388-400).
+//
+// The reference is eager PyTorch: every elementary op rounds to fp32 on its own, so every
+// product and sum below is spelled with __fmul_rn/__fadd_rn/__fsub_rn (never contracted);
+// torch.linspace is the one place where ATen itself fuses (see linspace01).
+#pragma once
+#include "common.cuh"
+
+struct SamplerParams {
+    const float *pts;
+    const float *rays;
+    const float *t_rand;
+    uint32_t n_rays, n_samples;
+    int32_t perturb;
+    uint32_t n1, n2, n3, i0, i1;
+    double s1, s2, s3;
+    float bound, inv_2bound, clamp;
+    float lin_step;  // fl(1 / (S-1))
+};
+
+#ifdef __CUDACC__
+
+// torch.linspace(0, 1, S)[i]: i < S/2 ? fma(step, i, 0) : fma(-step, S-1-i, 1)   (render.py:91)
+__device__ __forceinline__ float linspace01(uint32_t i, uint32_t S, float step) {
+    if (S <= 1) return 0.f;
+    return i < S / 2 ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(S - 1 - i), 1.0f);
+}
+
+// z = near*(1-t) + far*t            (render.py:92)
+__device__ __forceinline__ float z_uniform(float near, float far, uint32_t i, uint32_t S, float step) {
+    const float t = linspace01(i, S, step);
+    return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
+}
+
+// perturbed sample i of a ray (render.py:95-100): lower + (upper-lower)*t_rand
+__device__ __forceinline__ float z_sample(float near, float far, uint32_t i, uint32_t S, float step, bool perturb,
+                                          const float *__restrict__ t_rand_row) {
+    const float zi = z_uniform(near, far, i, S, step);
+    if (!perturb) return zi;
+    float lower = zi, upper = zi;
+    if (i > 0) lower = __fmul_rn(0.5f, __fadd_rn(zi, z_uniform(near, far, i - 1, S, step)));
+    if (i + 1 < S) upper = __fmul_rn(0.5f, __fadd_rn(z_uniform(near, far, i + 1, S, step), zi));
+    return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(t_rand_row + i)));
+}
+
+struct RayRegs {
+    float o[3], d[3], near, far, norm;
+};
+
+__device__ __forceinline__ RayRegs load_ray(const float *__restrict__ rays, uint32_t r) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * (size_t)r);
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * (size_t)r + 1);
+    RayRegs R;
+    R.o[0] = a.x; R.o[1] = a.y; R.o[2] = a.z;
+    R.d[0] = a.w; R.d[1] = b.x; R.d[2] = b.y;
+    R.near = b.z; R.far = b.w;
+    R.norm = sqrtf(__fmaf_rn(R.d[2], R.d[2], __fmaf_rn(R.d[1], R.d[1], __fmul_rn(R.d[0], R.d[0]))));  // render.py:194
+    return R;
+}
+
+// pts = clamp(o + d*z, -c, c)       (render.py:103-105)
+__device__ __forceinline__ float ray_point(float o, float d, float z, float c) {
+    return fminf(fmaxf(__fadd_rn(o, __fmul_rn(d, z)), -c), c);
+}
+
+// np.linspace(-s, s, n)[i] in float64, then the fp32 cast of tigre.py:277
+__device__ __forceinline__ float voxel_coord(uint32_t i, uint32_t n, double s) {
+    if (n == 1) return (float)(-s);
+    if (i == n - 1) return (float)s;
+    const double step = __ddiv_rn(__dsub_rn(s, -s), (double)(n - 1));
+    return (float)__dadd_rn(__dmul_rn((double)i, step), -s);
+}
+
+// Fetch point p of the launch (world coordinates). For RAYS also yields ray/sample index.
+template <int SRC>
+__device__ __forceinline__ void fetch_point(const SamplerParams &sp, uint64_t p, float (&x)[3]) {
+    if constexpr (SRC == NAFB_SRC_POINTS) {
+        x[0] = __ldg(sp.pts + 3 * p);
+        x[1] = __ldg(sp.pts + 3 * p + 1);
+        x[2] = __ldg(sp.pts + 3 * p + 2);
+    } else if constexpr (SRC == NAFB_SRC_RAYS) {
+        const uint32_t r = (uint32_t)(p / sp.n_samples), i = (uint32_t)(p - (uint64_t)r * sp.n_samples);
+        const RayRegs R = load_ray(sp.rays, r);
+        const float z = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
+                                 sp.t_rand ? sp.t_rand + (size_t)r * sp.n_samples : nullptr);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = ray_point(R.o[d], R.d[d], z, sp.clamp);
+    } else {
+        const uint64_t plane = (uint64_t)sp.n2 * sp.n3;
+        const uint32_t i = sp.i0 + (uint32_t)(p / plane);
+        const uint32_t rem = (uint32_t)(p - (uint64_t)(i - sp.i0) * plane);
+        const uint32_t j = rem / sp.n3, k = rem - j * sp.n3;
+        x[0] = voxel_coord(i, sp.n1, sp.s1);
+        x[1] = voxel_coord(j, sp.n2, sp.s2);
+        x[2] = voxel_coord(k, sp.n3, sp.s3);
+    }
+}
+
+// delta_i * |d| of raw2outputs (render.py:192-194): (z[i+1]-z[i]) * norm, last = 1e-10 * norm
+__device__ __forceinline__ float ray_delta(const SamplerParams &sp, const RayRegs &R, uint32_t r, uint32_t i) {
+    const uint32_t S = sp.n_samples;
+    const float *tr = sp.t_rand ? sp.t_rand + (size_t)r * S : nullptr;
+    float dist;
+    if (i + 1 < S) {
+        const float z0 = z_sample(R.near, R.far, i, S, sp.lin_step, sp.perturb != 0, tr);
+        const float z1 = z_sample(R.near, R.far, i + 1, S, sp.lin_step, sp.perturb != 0, tr);
+        dist = __fsub_rn(z1, z0);
+    } else {
+        dist = 1e-10f;
+    }
+    return __fmul_rn(dist, R.norm);
+}
+
+// normalisation of HashEncoder.forward (hashgrid.py:125) as ATen's CUDA kernels evaluate it:
+// (x + size) is one add; "/ (2*size)" with a python-scalar divisor is a multiply by fl(1/fl(2*size)).
+__device__ __forceinline__ float normalise01(float x, float bound, float inv_2bound) {
+    return __fmul_rn(__fadd_rn(x, bound), inv_2bound);
+}
+
+#endif  // __CUDACC__
+
+// host: ABI struct -> kernel parameter block
+static inline int nafb_make_sampler_params(const nafb_sampler *s, int src, SamplerParams *out, uint64_t *n_points) {
+    if (!s) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: null");
+    SamplerParams p{};
+    p.pts = s->pts; p.rays = s->rays; p.t_rand = s->t_rand;
+    p.n_rays = s->n_rays; p.n_samples = s->n_samples; p.perturb = s->perturb;
+    p.n1 = s->n1; p.n2 = s->n2; p.n3 = s->n3; p.i0 = s->i0; p.i1 = s->i1;
+    p.s1 = s->s1; p.s2 = s->s2; p.s3 = s->s3;
+    p.bound = s->bound;
+    p.inv_2bound = 1.0f / (2.0f * s->bound);   // see normalise01: fl(1 / fl(2*size)); the doubling is exact
+    p.clamp = s->clamp;
+    p.lin_step = s->n_samples > 1 ? 1.0f / (float)(s->n_samples - 1) : 0.f;
+    uint64_t n = 0;
+    switch (src) {
+        case NAFB_SRC_POINTS:
+            if (!s->pts) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: pts is null");
+            n = s->n_points;
+            break;
+        case NAFB_SRC_RAYS:
+            if (!s->rays || s->n_samples == 0) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: rays null or n_samples == 0");
+            if (s->perturb && !s->t_rand) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: perturb needs t_rand");
+            n = (uint64_t)s->n_rays * s->n_samples;
+            break;
+        case NAFB_SRC_VOXELS:
+            if (s->i1 > s->n1 || s->i0 > s->i1) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: bad voxel slab");
+            n = (uint64_t)(s->i1 - s->i0) * s->n2 * s->n3;
+            break;
+        default:
+            NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: unknown point source %d", src);
+    }
+    *out = p;
+    *n_points = n;
+    return NAFB_OK;
+}

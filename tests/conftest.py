@@ -14,12 +14,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def formula_table(n_entries: int, C: int, scale: float) -> np.ndarray:
-    """Same closed form as tests/golden/generate_golden.py::formula_table."""
-    i = np.arange(n_entries * C, dtype=np.uint64)
-    u = (i * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)
-    v = (u.astype(np.float64) / 4294967296.0 - 0.5) * 2.0 * scale
-    return v.astype(np.float32).reshape(n_entries, C)
+from helpers import formula_table  # noqa: E402,F401
 
 
 @pytest.fixture(scope="session")

@@ -28,17 +28,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
+sys.path.insert(0, os.path.dirname(HERE))
+from helpers import formula_table, make_rays  # noqa: E402
 from oracle import hashgrid as oh  # noqa: E402
 
 REF = "/root/reference"
-
-
-def formula_table(n_entries: int, C: int, scale: float) -> np.ndarray:
-    """Deterministic table: value(i) = ((i * 2654435761 mod 2^32) / 2^32 - 0.5) * 2 * scale, fp32."""
-    i = np.arange(n_entries * C, dtype=np.uint64)
-    u = (i * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)
-    v = (u.astype(np.float64) / 4294967296.0 - 0.5) * 2.0 * scale
-    return v.astype(np.float32).reshape(n_entries, C)
 
 
 def install_reference():
@@ -149,16 +143,6 @@ def _mlp_arrays(net, prefix=""):
         d[f"{prefix}W{i}"] = lin.weight.detach().numpy().copy()
         d[f"{prefix}b{i}"] = lin.bias.detach().numpy().copy()
     return d
-
-
-def make_rays(n, rng, near=0.90449, far=1.09551):
-    """Cone-like rays through the +-0.15 cube from a source 1 m away."""
-    ang = rng.uniform(0, 2 * np.pi, n)
-    o = np.stack([np.cos(ang), np.sin(ang), rng.uniform(-0.02, 0.02, n)], -1)
-    tgt = rng.uniform(-0.12, 0.12, (n, 3))
-    d = tgt - o
-    d = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(1.0, 1.0002, (n, 1))
-    return np.concatenate([o, d, np.full((n, 1), near), np.full((n, 1), far)], -1).astype(np.float32)
 
 
 def gen_render_fixtures():

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import formula_table
+from helpers import formula_table, make_rays  # noqa: F401
 from oracle import hashgrid as oh
 from oracle import naf
 

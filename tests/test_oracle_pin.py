@@ -4,7 +4,7 @@ inputs.  Skipped where oracle/_ref was not built (it is built in the container t
 import numpy as np
 import pytest
 
-from conftest import formula_table
+from helpers import formula_table, make_rays  # noqa: F401
 from oracle import hashgrid as oh
 
 pytestmark = pytest.mark.skipif(not oh.have_ref(), reason="oracle/_ref not built")
