@@ -588,12 +588,12 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
     int rc = nafb_make_grid_params(grid, &gp);
     if (rc) return rc;
     if ((rc = check_mlp(grid, mlp))) return rc;
-    if (!dsigma_or_dacc || !grads || !workspace) NAFB_FAIL(NAFB_ERR_INVALID, "density_backward: null pointer");
     if (src == NAFB_SRC_VOXELS) NAFB_FAIL(NAFB_ERR_UNSUPPORTED, "density_backward: the voxel source is forward only");
     SamplerParams sp;
     uint64_t P = 0;
     if ((rc = nafb_make_sampler_params(smp, src, &sp, &P))) return rc;
     if (P == 0) return NAFB_OK;
+    if (!dsigma_or_dacc || !grads || !workspace) NAFB_FAIL(NAFB_ERR_INVALID, "density_backward: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL(S_, C_) launch_bwd<S_, C_>(gp, *mlp, sp, P, dsigma_or_dacc, grad_table, *grads, (float *)workspace, s)
     switch (gp.C) {

@@ -256,6 +256,7 @@ int nafb_hash_encode_forward(const nafb_grid *grid, const float *inputs, float *
     GridParams gp;
     int rc = nafb_make_grid_params(grid, &gp);
     if (rc) return rc;
+    if (B == 0) return NAFB_OK;
     if (!inputs || !outputs) NAFB_FAIL(NAFB_ERR_INVALID, "hash_encode_forward: null pointer");
     if (calc_grad_inputs && !dy_dx) NAFB_FAIL(NAFB_ERR_INVALID, "hash_encode_forward: dy_dx required when calc_grad_inputs");
     if (out_layout != NAFB_LAYOUT_LBC && out_layout != NAFB_LAYOUT_BLC) NAFB_FAIL(NAFB_ERR_INVALID, "hash_encode_forward: bad layout");
@@ -272,6 +273,7 @@ int nafb_hash_encode_backward(const nafb_grid *grid, const float *grad, const fl
     GridParams gp;
     int rc = nafb_make_grid_params(grid, &gp);
     if (rc) return rc;
+    if (B == 0) return NAFB_OK;
     if (!grad || !inputs || !grad_table) NAFB_FAIL(NAFB_ERR_INVALID, "hash_encode_backward: null pointer");
     if (calc_grad_inputs && (!dy_dx || !grad_inputs)) NAFB_FAIL(NAFB_ERR_INVALID, "hash_encode_backward: dy_dx/grad_inputs required");
     if (grad_layout != NAFB_LAYOUT_LBC && grad_layout != NAFB_LAYOUT_BLC) NAFB_FAIL(NAFB_ERR_INVALID, "hash_encode_backward: bad layout");

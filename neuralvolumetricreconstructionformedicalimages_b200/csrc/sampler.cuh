@@ -136,13 +136,13 @@ static inline int nafb_make_sampler_params(const nafb_sampler *s, int src, Sampl
     uint64_t n = 0;
     switch (src) {
         case NAFB_SRC_POINTS:
-            if (!s->pts) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: pts is null");
             n = s->n_points;
+            if (n && !s->pts) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: pts is null");
             break;
         case NAFB_SRC_RAYS:
-            if (!s->rays || s->n_samples == 0) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: rays null or n_samples == 0");
-            if (s->perturb && !s->t_rand) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: perturb needs t_rand");
             n = (uint64_t)s->n_rays * s->n_samples;
+            if (n && !s->rays) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: rays is null");
+            if (n && s->perturb && !s->t_rand) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: perturb needs t_rand");
             break;
         case NAFB_SRC_VOXELS:
             if (s->i1 > s->n1 || s->i0 > s->i1) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: bad voxel slab");

@@ -35,6 +35,48 @@ def _round_up(n, m):
     return (n + m - 1) // m * m
 
 
+class _NoTimer:
+    def __call__(self, name):
+        return self
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class EventTimer:
+    """CUDA-event stopwatch around individual launches on the current stream (profiling runs only)."""
+
+    def __init__(self):
+        self.spans = []
+        self._name = None
+
+    def __call__(self, name):
+        self._name = name
+        return self
+
+    def __enter__(self):
+        self._e0 = torch.cuda.Event(enable_timing=True)
+        self._e0.record()
+        return self
+
+    def __exit__(self, *a):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.spans.append((self._name, self._e0, e1))
+        return False
+
+    def summary(self):
+        """name -> (mean ms, count); call after torch.cuda.synchronize()."""
+        acc = {}
+        for name, e0, e1 in self.spans:
+            t, c = acc.get(name, (0.0, 0))
+            acc[name] = (t + e0.elapsed_time(e1), c + 1)
+        return {k: (t / c, c) for k, (t, c) in acc.items()}
+
+
 class NAFEngine:
     def __init__(self, net: DensityNetwork, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, n_samples=192, perturb=True, loss_chunk=None,
                  use_cuda_graph=True, process_group=None):
@@ -83,28 +125,59 @@ class NAFEngine:
         self.grad_mlp = self._grad_views[1:]
 
     # ------------------------------------------------------------------ one training step
-    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc):
+    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None):
         L_ = _lib.lib()
+        tm = timer or _NoTimer()
         N = rays.shape[0]
-        acc.zero_()
+        with tm("zero_acc"):
+            acc.zero_()
         grid = self.meta.grid(self.table)
         mlp = self.meta.mlp(self.mlp_params)
         smp = self.meta.sampler(rays=rays.data_ptr(), t_rand=t_rand.data_ptr() if self.perturb else None, n_rays=N,
                                 n_samples=self.n_samples, perturb=int(self.perturb))
         st = _lib.stream_ptr()
-        _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, None, _lib.ptr(acc),
-                                           None, None, None, st))
+        with tm("density_fwd"):
+            _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, None, _lib.ptr(acc),
+                                               None, None, None, st))
         chunk = int(self.loss_chunk or 0)
-        _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), st))
-        density_backward(self.meta, self.table, self.mlp_params, dacc, self.grad_table, self.grad_mlp, rays=rays, t_rand=t_rand,
-                         n_samples=self.n_samples, perturb=self.perturb)
+        with tm("mse_loss"):
+            _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), st))
+        with tm("density_bwd"):
+            density_backward(self.meta, self.table, self.mlp_params, dacc, self.grad_table, self.grad_mlp, rays=rays, t_rand=t_rand,
+                             n_samples=self.n_samples, perturb=self.perturb)
 
-    def _adam(self):
+    def _adam(self, timer=None):
         L_ = _lib.lib()
         self.step_count += 1
-        _lib.check(L_.nafb_adam_step(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-                                     self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
-                                     1.0 / self.world_size, 1, _lib.stream_ptr()))
+        with (timer or _NoTimer())("adam"):
+            _lib.check(L_.nafb_adam_step(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                         _lib.ptr(self.exp_avg_sq), self.n_params, self.lr, self.betas[0], self.betas[1], self.eps,
+                                         self.step_count, 1.0 / self.world_size, 1, _lib.stream_ptr()))
+
+    # kernels of this library launched by one train_step (density_fwd, mse_loss, density_bwd, reduce_partials, adam)
+    LAUNCHES_PER_STEP = 5
+
+    def profiled_step(self, rays, projs, mask, t_rand, timer):
+        """Same work as train_step, launched eagerly (no graph) with a CUDA-event pair around every kernel."""
+        N = rays.shape[0]
+        s = self._get_static(N, mask is not None)
+        with torch.cuda.device(self.device):
+            s["rays"].copy_(rays.reshape(N, 8))
+            s["projs"].copy_(projs.reshape(N))
+            if mask is not None:
+                s["mask"].copy_(mask.reshape(N))
+            if self.perturb:
+                with timer("t_rand"):
+                    if t_rand is None:
+                        s["t_rand"].uniform_(0.0, 1.0)
+                    else:
+                        s["t_rand"].copy_(t_rand)
+            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], timer)
+            if self.world_size > 1:
+                with timer("all_reduce"):
+                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+            self._adam(timer)
+        return s["loss"][0]
 
     def _get_static(self, N, with_mask):
         key = (N, with_mask)

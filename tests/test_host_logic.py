@@ -1,0 +1,133 @@
+"""CPU tests of the host-side logic of the product package (no kernel launches):
+geometry vs the reference fixtures, API surface vs the reference signatures, C-ABI exports."""
+import ctypes
+import inspect
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import neuralvolumetricreconstructionformedicalimages_b200 as pkg
+from neuralvolumetricreconstructionformedicalimages_b200 import _lib
+from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_GEO = dict(DSD=1500.0, DSO=1000.0, nDetector=[10, 6], dDetector=[1.5, 2.0], nVoxel=[8, 6, 4], dVoxel=[1.0, 2.0, 1.5],
+                offOrigin=[0, 0, 0], offDetector=[0.5, -1.0], accuracy=0.5, filter=None)
+
+
+@pytest.mark.parametrize("mode,tilt", [("cone", 0), ("parallel", 29), ("parallel", 0), ("cone", 10)])
+def test_rays_bit_identical_to_reference(golden, mode, tilt):
+    fx = golden("geometry.npz")
+    geo = G.ConeGeometry(dict(BASE_GEO, mode=mode, tilt_angle=tilt))
+    tag = f"{mode}_t{tilt}"
+    poses = np.stack([G.angle2pose(geo.DSO, a, tilt) for a in fx["angles"]])
+    np.testing.assert_allclose(poses, fx[f"poses_{tag}"], rtol=0, atol=1e-15)
+    rays = G.get_rays(fx["angles"], geo).numpy()
+    assert np.array_equal(rays.view(np.uint32), fx[f"rays_{tag}"].view(np.uint32))
+
+
+def test_near_far_voxels(golden):
+    fx = golden("geometry.npz")
+    geo = G.ConeGeometry(dict(BASE_GEO, mode="cone"))
+    assert np.array_equal(np.asarray(G.get_near_far(geo)), fx["near_far"])
+    assert np.array_equal(G.get_voxels(geo), fx["voxels"])
+    chest = G.ConeGeometry(G.chest50_like())
+    assert np.array_equal(np.asarray(G.get_near_far(chest)), fx["near_far_chest"])
+    r = G.rays_with_near_far([0.0, 1.0], G.ConeGeometry(dict(BASE_GEO, mode="cone")))
+    assert r.shape == (2, 6, 10, 8)
+
+
+def test_operator_signatures_match_reference():
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder import get_encoder
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder.freqencoder import FreqEncoder
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder.hashgrid import HashEncoder
+    from neuralvolumetricreconstructionformedicalimages_b200.loss import calc_mse_loss
+    from neuralvolumetricreconstructionformedicalimages_b200.network import DensityNetwork, get_network
+    from neuralvolumetricreconstructionformedicalimages_b200.render import raw2outputs, render, run_network, sample_pdf
+
+    with open(os.path.join(ROOT, "tests", "golden", "signatures.json")) as f:
+        ref = json.load(f)
+    ours = {"render": render, "run_network": run_network, "raw2outputs": raw2outputs, "sample_pdf": sample_pdf, "get_encoder": get_encoder,
+            "get_network": get_network, "DensityNetwork.__init__": DensityNetwork.__init__, "DensityNetwork.forward": DensityNetwork.forward,
+            "FreqEncoder.__init__": FreqEncoder.__init__, "calc_mse_loss": calc_mse_loss, "HashEncoder.__init__": HashEncoder.__init__,
+            "HashEncoder.forward": HashEncoder.forward}
+    strip = lambda s: re.sub(r" at 0x[0-9a-f]+", "", s)  # noqa: E731
+    for name, fn in ours.items():
+        assert strip(str(inspect.signature(fn))) == strip(ref[name]), name
+
+
+def test_module_surface_and_state_dict():
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder import get_encoder
+    from neuralvolumetricreconstructionformedicalimages_b200.network import get_network
+
+    enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
+    assert enc.output_dim == 32 and enc.offsets.dtype == torch.int32 and int(enc.offsets[-1]) == 7131219
+    assert float(enc.embeddings.abs().max()) <= 1e-4
+    net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid")
+    sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "encoder.embeddings": (7131219, 2), "layers.0.weight": (32, 32), "layers.0.bias": (32,), "layers.1.weight": (32, 32),
+        "layers.1.bias": (32,), "layers.2.weight": (32, 64), "layers.2.bias": (32,), "layers.3.weight": (1, 32), "layers.3.bias": (1,)}
+    assert net.fused_meta() is not None and net.in_dim == 32 and net.bound == 0.3
+    fe = get_encoder("frequency", multires=6)
+    assert fe.output_dim == 39
+    assert get_network("mlp")(fe, num_layers=4, hidden_dim=32, skips=[2]).fused_meta() is None
+    with pytest.raises(NotImplementedError):
+        get_encoder("sphere")
+    with pytest.raises(NotImplementedError):
+        get_network("cnn")
+    with pytest.raises(NotImplementedError):
+        get_network("mlp")(fe, last_activation="softplus")
+    ident, dim = get_encoder("None", input_dim=3)
+    assert dim == 3 and ident(5) == 5
+
+
+def test_no_cpu_fallback():
+    """The product must fail loudly off-GPU instead of computing on the host."""
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder import get_encoder
+    from neuralvolumetricreconstructionformedicalimages_b200.loss import calc_mse_loss
+    from neuralvolumetricreconstructionformedicalimages_b200.render import render
+
+    enc = get_encoder("hashgrid", num_levels=2, log2_hashmap_size=8)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        enc(torch.zeros(4, 3), 1)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        calc_mse_loss({"loss": 0.0}, torch.zeros(3), torch.zeros(3))
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        render(torch.zeros(4, 8), None, None, 8, 0, False, 1024, 0.0)
+    # and nothing under the package imports the oracle
+    for dirpath, _, files in os.walk(os.path.dirname(pkg.__file__)):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
+
+
+def test_c_abi_exports_every_declared_symbol():
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "nafb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(nafb_[a-z0-9_]+)\s*\(", header)))
+    assert declared == _lib.exported_symbols()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.nafb_abi_version() == 1
+    # struct layouts agree with the C header (sizes computed by the C compiler)
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include "nafb200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(nafb_grid), sizeof(nafb_mlp), sizeof(nafb_mlp_grads), sizeof(nafb_sampler));}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert sizes == [ctypes.sizeof(_lib.Grid), ctypes.sizeof(_lib.Mlp), ctypes.sizeof(_lib.MlpGrads), ctypes.sizeof(_lib.Sampler)]
+    # argument validation happens before any launch: safe to exercise without a GPU
+    assert L.nafb_adam_step(None, None, None, None, 4, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, 1, None) == _lib.ERR_INVALID
+    assert b"null pointer" in L.nafb_last_error()
+    offs = np.asarray([0, 8, 16], np.int32)
+    g = _lib.Grid(1, offs.ctypes.data, 3, 3, 2, 4)
+    assert L.nafb_hash_encode_forward(ctypes.byref(g), 1, 1, 4, 0, 0, None, None) == _lib.ERR_UNSUPPORTED
+    assert L.nafb_last_error() == b"GridEncoding: C must be 1, 2, 4, or 8."
