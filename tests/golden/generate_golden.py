@@ -52,7 +52,11 @@ def install_reference():
 
     class HashEncoder(oh.OracleHashEncoder):
         def __init__(self, input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19):
-            super().__init__(input_dim, num_levels, level_dim, base_resolution, log2_hashmap_size, use_ref=True, normalise="div")
+            # hashgrid.py:125 `(inputs + size) / (2 * size)` is evaluated by ATen's CUDA div kernel as a
+            # multiply by fl(1 / fl(2*size)) (python-scalar divisor); the reference only ever runs this
+            # module on CUDA, so the fixtures follow that evaluation (checked against torch on the
+            # GPU by tests/test_gpu_parity.py::test_aten_cuda_assumptions).
+            super().__init__(input_dim, num_levels, level_dim, base_resolution, log2_hashmap_size, use_ref=True, normalise="mul_recip")
 
     stub.HashEncoder = HashEncoder
     sys.modules["src.encoder.hashencoder"] = stub

@@ -108,7 +108,7 @@ def test_render_freq(golden):
 
 
 def _chest_net(fx, table_scale=0.5, **kw):
-    enc = oh.OracleHashEncoder(3, 16, 2, 16, 19, use_ref=False, normalise="div")
+    enc = oh.OracleHashEncoder(3, 16, 2, 16, 19, use_ref=False, normalise="mul_recip")  # as the fixtures (CUDA evaluation)
     with torch.no_grad():
         enc.embeddings.copy_(torch.from_numpy(formula_table(enc.embeddings.shape[0], 2, table_scale)))
     cfg = dict(bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid")
