@@ -170,6 +170,13 @@ int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
                    float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad,
                    nafb_stream_t stream);
 
+/* ------------------------------------------------------------------ diagnostics
+ * Known-answer test of the tcgen05 plumbing (one 128-row tile, bf16x3 split precision):
+ *   D1 [128,32] = A[:, :32] . W[:, :32]^T ; D2 [128,64] = A[:, :32] . W ; D3 [128,32] = A^T . X
+ * with A [128,128], X [128,32], W [32,64] fp32 row-major. */
+int nafb_selftest_umma(const float *A, const float *X, const float *W, float *D1, float *D2, float *D3,
+                       nafb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
