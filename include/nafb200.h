@@ -170,6 +170,11 @@ int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
                    float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad,
                    nafb_stream_t stream);
 
+/* Arithmetic of the fused density kernels: 0 (default) = tcgen05 tensor cores with bf16x3 split
+ * operands and fp32 TMEM accumulation wherever the configuration allows (4 x 32 MLP, skip at 2),
+ * 1 = fp32 SIMT FMAs everywhere (bit-reproducible dot-product order; the general-shape path). */
+int nafb_set_mlp_mode(int mode);
+
 /* ------------------------------------------------------------------ diagnostics
  * Known-answer test of the tcgen05 plumbing (one 128-row tile, bf16x3 split precision):
  *   D1 [128,32] = A[:, :32] . W[:, :32]^T ; D2 [128,64] = A[:, :32] . W ; D3 [128,32] = A^T . X

@@ -19,6 +19,15 @@
 #include "common.cuh"
 #include "sampler.cuh"
 
+// tcgen05 edition (density_tc.cu)
+bool nafb_tc_config_ok(const nafb_grid *grid, const nafb_mlp *mlp);
+int nafb_tc_bwd_grid(uint64_t n_tiles);
+int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
+                       float *pts, int32_t *flags, cudaStream_t s);
+int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
+                       float *grad_table, float *partials, int grid, cudaStream_t s);
+static int g_mlp_mode = 0;  // 0: tensor cores when the configuration allows, 1: fp32 SIMT everywhere
+
 namespace {
 
 constexpr int TILE = 128;  // points per CTA tile == threads per CTA
@@ -571,9 +580,16 @@ int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_
     if (P == 0) return NAFB_OK;
     if (src != NAFB_SRC_RAYS && (acc || z_vals || pts_out)) NAFB_FAIL(NAFB_ERR_INVALID, "density_forward: acc/z_vals/pts_out need the RAYS source");
     cudaStream_t s = (cudaStream_t)stream;
+    if (g_mlp_mode == 0 && nafb_tc_config_ok(grid, mlp)) return nafb_launch_fwd_tc(gp, *mlp, sp, src, P, sigma, acc, z_vals, pts_out, flags, s);
 #define CALL(S_, C_) launch_fwd<S_, C_>(gp, *mlp, sp, P, sigma, acc, z_vals, pts_out, flags, s)
     DISPATCH_SRC_C(src, gp.C, CALL);
 #undef CALL
+}
+
+int nafb_set_mlp_mode(int mode) {
+    if (mode != 0 && mode != 1) NAFB_FAIL(NAFB_ERR_INVALID, "set_mlp_mode: mode must be 0 (tensor cores) or 1 (fp32 SIMT)");
+    g_mlp_mode = mode;
+    return NAFB_OK;
 }
 
 uint64_t nafb_density_backward_workspace_bytes(const nafb_mlp *mlp) {
@@ -595,6 +611,14 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
     if (P == 0) return NAFB_OK;
     if (!dsigma_or_dacc || !grads || !workspace) NAFB_FAIL(NAFB_ERR_INVALID, "density_backward: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
+    if (g_mlp_mode == 0 && nafb_tc_config_ok(grid, mlp)) {
+        const int grid_tc = nafb_tc_bwd_grid((P + TILE - 1) / TILE);
+        if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, grid_tc, s))) return rc;
+        const MlpLayout lo = make_layout(*mlp);
+        k_reduce_partials<<<(lo.total + 255) / 256, 256, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
+        NAFB_CHECK_LAUNCH("density_backward(reduce)");
+        return NAFB_OK;
+    }
 #define CALL(S_, C_) launch_bwd<S_, C_>(gp, *mlp, sp, P, dsigma_or_dacc, grad_table, *grads, (float *)workspace, s)
     switch (gp.C) {
         case 1: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 1) : CALL(NAFB_SRC_RAYS, 1);

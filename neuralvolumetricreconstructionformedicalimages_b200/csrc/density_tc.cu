@@ -1,0 +1,693 @@
+// density_tc.cu -- tcgen05 edition of the fused "hash-grid encoder + density MLP" kernels for the
+// configuration every shipped YAML uses: L*C == 32 encoding, 4 layers x 32 hidden, skip at
+// layer 2, out_dim 1 (reference src/network/network.py:34-58, config/*.yaml).
+//
+// One CTA = 256 threads = one 128-point tile at a time (persistent over tiles).
+//   thread t:  row r = t & 127 (sample point, == TMEM lane), half = t >> 7 owns feature
+//              columns [16*half, 16*half+16) of every 32-wide activation of its point.
+// Activations are written ONCE, by the thread that owns the point, as bf16 (hi, lo) pairs in the
+// canonical no-swizzle UMMA layout (umma.cuh) and consumed in place by the tensor core:
+//   forward      h_l   = lrelu(X . W_l^T + b)        A = X  (K-major)      B = W_l  (K-major)
+//   input grad   dX    = G . W_l                     A = G  (K-major)      B = W_l  (MN-major view)
+//   weight grad  dW_l += G^T . X   (over 128 points) A = G  (MN-major view) B = X   (MN-major view)
+// Accumulators live in TMEM (fp32); weight gradients stay in TMEM across all tiles of the CTA and
+// are read out once.  Products are bf16x3 (hi*hi + hi*lo + lo*hi): |rel err| ~ 2^-16 per product.
+// Bias, LeakyReLU, the 1-wide head, its gradient and the bias / head-weight gradients are fp32
+// SIMT work in the epilogues (TMEM -> registers -> shared memory operand of the next MMA).
+#include "common.cuh"
+#include "sampler.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int NT = 256;
+constexpr uint32_t LBO = 128;  // bytes between adjacent 8-column chunks of a row group
+
+// ---- weights in shared memory (bf16 hi / lo, rows = output feature, chunks along the input)
+constexpr uint32_t W0_OFF = 0, W0_SBO = 512;      // 32 x 32
+constexpr uint32_t W1_OFF = 2048, W1_SBO = 512;   // 32 x 32
+constexpr uint32_t W2_OFF = 4096, W2_SBO = 1024;  // 32 x 64
+constexpr uint32_t W_HALF = 8192;                 // bytes per (hi | lo) weight image
+
+struct SmallParams {   // fp32: biases of the hidden layers, head weights + bias
+    float b0[32], b1[32], b2[32], w3[32], b3;
+};
+
+__device__ __forceinline__ void load_weight_images(const nafb_mlp &mp, uint8_t *w_hi, uint8_t *w_lo, SmallParams *sp) {
+    // one 16-byte chunk (8 consecutive inputs of one output row) per iteration
+    auto fill = [&](const float *__restrict__ W, int in_dim, uint32_t off, uint32_t sbo) {
+        const int chunks = in_dim / 8;
+        for (int i = threadIdx.x; i < 32 * chunks; i += blockDim.x) {
+            const int row = i / chunks, c = i - row * chunks;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(W + row * in_dim + c * 8 + k);
+            umma::store_chunk_split(w_hi, w_lo, off + umma::canon_off(row, c, LBO, sbo), v);
+        }
+    };
+    fill(mp.W[0], 32, W0_OFF, W0_SBO);
+    fill(mp.W[1], 32, W1_OFF, W1_SBO);
+    fill(mp.W[2], 64, W2_OFF, W2_SBO);
+    if (threadIdx.x < 32) {
+        sp->b0[threadIdx.x] = __ldg(mp.b[0] + threadIdx.x);
+        sp->b1[threadIdx.x] = __ldg(mp.b[1] + threadIdx.x);
+        sp->b2[threadIdx.x] = __ldg(mp.b[2] + threadIdx.x);
+        sp->w3[threadIdx.x] = __ldg(mp.W[3] + threadIdx.x);
+        if (threadIdx.x == 0) sp->b3 = __ldg(mp.b[3]);
+    }
+}
+
+// gather the 16 encoding features [16*half, 16*half+16) of one point into two chunks
+template <int C>
+__device__ __forceinline__ void gather_half(const GridParams &gp, const float (&x01)[3], int half, float (&enc)[16]) {
+    constexpr int LH = 16 / C;  // levels per half
+#pragma unroll
+    for (int li = 0; li < LH; ++li) {
+        const int l = half * LH + li;
+        const LevelParams lp = gp.lv[l];
+        const float *__restrict__ tab = gp.table + (size_t)lp.offset * C;
+        uint32_t g[3];
+        float f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
+        float v[8][C];
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx)
+            load_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v[idx]);
+        float res[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) res[c] = 0.f;
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            float w = 1.0f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
+#pragma unroll
+            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[idx][c], res[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) enc[li * C + c] = res[c];
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void scatter_half(const GridParams &gp, const float (&x01)[3], int half, const float (&genc)[16], float *grad_table) {
+    constexpr int LH = 16 / C;
+#pragma unroll
+    for (int li = 0; li < LH; ++li) {
+        const int l = half * LH + li;
+        const LevelParams lp = gp.lv[l];
+        float *tab = grad_table + (size_t)lp.offset * C;
+        uint32_t g[3];
+        float f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            float w = 1.0f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __fmul_rn(w, genc[li * C + c]);
+            red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v);
+        }
+    }
+}
+
+// write this thread's 16 values (two chunks) of a 32-wide block starting at chunk `chunk0`
+__device__ __forceinline__ void store_half_row(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo, const float (&v)[16]) {
+    umma::store_chunk_split(hi, lo, umma::canon_off(row, chunk0 + 2 * half, LBO, sbo), v);
+    umma::store_chunk_split(hi, lo, umma::canon_off(row, chunk0 + 2 * half + 1, LBO, sbo), v + 8);
+}
+
+// sign of the stored activations (hi part is enough): slope of LeakyReLU at h
+__device__ __forceinline__ void lrelu_slopes(const uint8_t *hi, uint32_t row, uint32_t chunk0, int half, uint32_t sbo, float (&s)[16]) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(hi + umma::canon_off(row, chunk0 + 2 * half + c, LBO, sbo));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // bf16 > 0  <=>  sign bit clear and not zero
+            const uint32_t a = w[i] & 0xFFFFu, b = w[i] >> 16;
+            s[c * 8 + 2 * i] = (a != 0u && !(a & 0x8000u)) ? 1.0f : 0.01f;
+            s[c * 8 + 2 * i + 1] = (b != 0u && !(b & 0x8000u)) ? 1.0f : 0.01f;
+        }
+    }
+}
+
+// column sums over the 32 lanes of a warp of 16 per-lane values: afterwards lane (j & 15) and
+// lane (j & 15) + 16 hold the sum of column j.  Recursive halving: 8+4+2+1+1 = 16 shuffles.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], unsigned lane) {
+    float a[8];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = up ? v[i] : v[i + 8];
+            const float keep = up ? v[i + 8] : v[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    float b[4];
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = up ? a[i] : a[i + 4];
+            const float keep = up ? a[i + 4] : a[i];
+            b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    float c[2];
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = up ? b[i] : b[i + 2];
+            const float keep = up ? b[i + 2] : b[i];
+            c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    float d;
+    {
+        const bool up = lane & 2;
+        const float send = up ? c[0] : c[1];
+        const float keep = up ? c[1] : c[0];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;  // column index held by this lane: colsum_index(lane)
+}
+// which of the 16 columns ends up in `lane` after warp_colsum16
+__device__ __forceinline__ int colsum_index(unsigned lane) {
+    return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+
+struct TileCtl {
+    uint64_t mbar;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+// ================================================================================ forward
+// smem: X_hi | X_lo : 128 rows x 8 chunks [enc(0-3) | h(4-7)], SBO 1024 -> 16 KB each
+constexpr uint32_t FX_SBO = 1024, FX_HALF = 16384;
+constexpr uint32_t FWD_SMEM = 2 * FX_HALF + 2 * W_HALF + sizeof(SmallParams) + sizeof(TileCtl) + TILE * sizeof(float) + 128;
+
+template <int SRC, int C>
+__global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
+                                                          float *__restrict__ sigma, float *__restrict__ acc_out, float *__restrict__ z_out,
+                                                          float *__restrict__ pts_out, int32_t *__restrict__ flags) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *X_hi = smem, *X_lo = X_hi + FX_HALF;
+    uint8_t *W_hi = X_lo + FX_HALF, *W_lo = W_hi + W_HALF;
+    SmallParams *small = reinterpret_cast<SmallParams *>(W_lo + W_HALF);
+    TileCtl *ctl = reinterpret_cast<TileCtl *>(reinterpret_cast<uint8_t *>(small) + ((sizeof(SmallParams) + 15) & ~15u));
+    float *xchg = reinterpret_cast<float *>(ctl + 1);  // [128] partial head dot products of half 1
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int r = t & 127, half = t >> 7;
+    load_weight_images(mp, W_hi, W_lo, small);
+    if (t == 0) {
+        umma::mbar_init(&ctl->mbar, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&ctl->tmem_base, 32);
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = ctl->tmem_base;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16u * half;
+    const uint32_t x_hi = umma::smem_u32(X_hi), x_lo = umma::smem_u32(X_lo), w_hi = umma::smem_u32(W_hi), w_lo = umma::smem_u32(W_lo);
+    constexpr uint32_t IDESC = umma::idesc_bf16(128, 32, 0, 0);
+    uint32_t phase = 0;
+    int bad = 0;
+
+    const uint64_t n_tiles = (P + TILE - 1) / TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t p = tile * TILE + r;
+        const bool valid = p < P;
+        float x[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            fetch_point<SRC>(sp, p, x);
+            if (!(x[0] >= -sp.bound && x[0] <= sp.bound && x[1] >= -sp.bound && x[1] <= sp.bound && x[2] >= -sp.bound && x[2] <= sp.bound))
+                bad |= 1;
+            if (SRC == NAFB_SRC_RAYS && pts_out && half == 0) {
+                pts_out[3 * p] = x[0]; pts_out[3 * p + 1] = x[1]; pts_out[3 * p + 2] = x[2];
+            }
+        }
+        float x01[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x01[d] = normalise01(x[d], sp.bound, sp.inv_2bound);
+        {
+            float enc[16];
+            gather_half<C>(gp, x01, half, enc);
+            store_half_row(X_hi, X_lo, r, 0, half, FX_SBO, enc);
+        }
+        // ---------------- layer 0: enc . W0^T
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem, umma::make_desc(x_hi, LBO, FX_SBO), umma::make_desc(x_lo, LBO, FX_SBO),
+                             umma::make_desc(w_hi + W0_OFF, LBO, W0_SBO), umma::make_desc(w_lo + W0_OFF, LBO, W0_SBO), 256, 256, 2, IDESC, false);
+            umma::commit(&ctl->mbar);
+        }
+        umma::mbar_wait(&ctl->mbar, phase);
+        phase ^= 1;
+        umma::fence_after_sync();
+        float v[16];
+        umma::tmem_ld16(taddr, v);
+        umma::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = leaky_relu(v[i] + small->b0[16 * half + i]);
+        store_half_row(X_hi, X_lo, r, 4, half, FX_SBO, v);
+        // ---------------- layer 1: h0 . W1^T
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem, umma::make_desc(x_hi + 4 * LBO, LBO, FX_SBO), umma::make_desc(x_lo + 4 * LBO, LBO, FX_SBO),
+                             umma::make_desc(w_hi + W1_OFF, LBO, W1_SBO), umma::make_desc(w_lo + W1_OFF, LBO, W1_SBO), 256, 256, 2, IDESC, false);
+            umma::commit(&ctl->mbar);
+        }
+        umma::mbar_wait(&ctl->mbar, phase);
+        phase ^= 1;
+        umma::fence_after_sync();
+        umma::tmem_ld16(taddr, v);
+        umma::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = leaky_relu(v[i] + small->b1[16 * half + i]);
+        store_half_row(X_hi, X_lo, r, 4, half, FX_SBO, v);
+        // ---------------- layer 2 (skip): [enc | h1] . W2^T, K = 64
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem, umma::make_desc(x_hi, LBO, FX_SBO), umma::make_desc(x_lo, LBO, FX_SBO),
+                             umma::make_desc(w_hi + W2_OFF, LBO, W2_SBO), umma::make_desc(w_lo + W2_OFF, LBO, W2_SBO), 256, 256, 4, IDESC, false);
+            umma::commit(&ctl->mbar);
+        }
+        umma::mbar_wait(&ctl->mbar, phase);
+        phase ^= 1;
+        umma::fence_after_sync();
+        umma::tmem_ld16(taddr, v);
+        umma::tmem_wait_ld();
+        // ---------------- head: sigma = act(w3 . lrelu(.) + b3), two half-row partial sums
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part = __fmaf_rn(leaky_relu(v[i] + small->b2[16 * half + i]), small->w3[16 * half + i], part);
+        if (half == 1) xchg[r] = part;
+        umma::fence_before_sync();   // orders the TMEM reads above before the next tile's MMAs
+        __syncthreads();
+        if (half == 0) {
+            const float s = (part + xchg[r]) + small->b3;
+            const float y = head_activation(s, mp.head);
+            if (valid) {
+                if (sigma) sigma[p] = y;
+                if (!(fabsf(y) <= 3.4028234e38f)) bad |= 2;
+            }
+            if constexpr (SRC == NAFB_SRC_RAYS) {
+                if (acc_out || z_out) {
+                    float contrib = 0.f;
+                    uint32_t ray = 0xffffffffu;
+                    if (valid) {
+                        ray = (uint32_t)(p / sp.n_samples);
+                        const uint32_t i = (uint32_t)(p - (uint64_t)ray * sp.n_samples);
+                        const RayRegs R = load_ray(sp.rays, ray);
+                        contrib = __fmul_rn(y, ray_delta(sp, R, ray, i));  // render.py:201
+                        if (z_out)
+                            z_out[p] = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
+                                                sp.t_rand ? sp.t_rand + (size_t)ray * sp.n_samples : nullptr);
+                    }
+                    if (acc_out) {  // warp-shuffle segmented reduction keyed by the ray id
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const float up = __shfl_down_sync(0xffffffffu, contrib, o);
+                            const uint32_t ur = __shfl_down_sync(0xffffffffu, ray, o);
+                            if (lane + o < 32 && ur == ray) contrib += up;
+                        }
+                        const uint32_t prev = __shfl_up_sync(0xffffffffu, ray, 1);
+                        if (valid && (lane == 0 || prev != ray)) atomicAdd(acc_out + ray, contrib);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // xchg / X are reused by the next tile
+    }
+    if (flags && bad) atomicOr(flags, bad);
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 32);
+}
+
+// ================================================================================ backward
+// smem: ALL_hi | ALL_lo : 128 rows x 20 chunks  [h0(0-3) | enc(4-7) | h1(8-11) | h2(12-15, unused) | G(16-19)], SBO 2560,
+// plus 1536 B of slack so that the 128-feature window starting at the G block stays inside the allocation.
+constexpr uint32_t BX_SBO = 2560, BX_HALF = 16 * 2560 + 1536;
+constexpr uint32_t CH_H0 = 0, CH_ENC = 4, CH_H1 = 8, CH_G = 16;
+constexpr uint32_t BWD_SMEM = 2 * BX_HALF + 2 * W_HALF + sizeof(SmallParams) + sizeof(TileCtl) + 2 * TILE * sizeof(float) + 8 * 80 * sizeof(float) + 128;
+// TMEM columns
+constexpr uint32_t T_S = 0, T_DENC = 32, T_DW0 = 64, T_DW1 = 96, T_DW2 = 128, T_COLS = 256;
+
+// offsets inside one CTA's slot of the partials workspace (floats) -- matches density.cu's MlpLayout for this net
+constexpr int PW0 = 0, PW1 = 1024, PW2 = 2048, PW3 = 4096, PB0 = 4128, PB1 = 4160, PB2 = 4192, PB3 = 4224, PTOTAL = 4228;
+
+template <int SRC, int C>
+__global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
+                                                          const float *__restrict__ dsig_or_dacc, float *__restrict__ grad_table,
+                                                          float *__restrict__ partials) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *A_hi = smem, *A_lo = A_hi + BX_HALF;
+    uint8_t *W_hi = A_lo + BX_HALF, *W_lo = W_hi + W_HALF;
+    SmallParams *small = reinterpret_cast<SmallParams *>(W_lo + W_HALF);
+    TileCtl *ctl = reinterpret_cast<TileCtl *>(reinterpret_cast<uint8_t *>(small) + ((sizeof(SmallParams) + 15) & ~15u));
+    float *xchg = reinterpret_cast<float *>(ctl + 1);  // [128] head partial dot products of half 1
+    float *xchg2 = xchg + TILE;                         // [128] head pre-activation gradients
+    float *wred = xchg2 + TILE;                         // [8 warps][80]: per-warp column sums flushed at the end
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int r = t & 127, half = t >> 7;
+    load_weight_images(mp, W_hi, W_lo, small);
+    // the slack / unused blocks are read (as don't-care rows) by the windowed dW MMAs: keep them finite
+    for (uint32_t i = t; i < 2 * BX_HALF / 16; i += NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (t == 0) {
+        umma::mbar_init(&ctl->mbar, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&ctl->tmem_base, T_COLS);
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = ctl->tmem_base;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t taddr = tmem + lane_base + 16u * half;
+    const uint32_t a_hi = umma::smem_u32(A_hi), a_lo = umma::smem_u32(A_lo), w_hi = umma::smem_u32(W_hi), w_lo = umma::smem_u32(W_lo);
+    constexpr uint32_t ID_FWD = umma::idesc_bf16(128, 32, 0, 0);   // K-major x K-major
+    constexpr uint32_t ID_DX = umma::idesc_bf16(128, 32, 0, 1);    // A K-major (G), B MN-major view of W
+    constexpr uint32_t ID_DW32 = umma::idesc_bf16(128, 32, 1, 1);  // both MN-major views, reduction over points
+    constexpr uint32_t ID_DW64 = umma::idesc_bf16(128, 64, 1, 1);
+    uint32_t phase = 0;
+    bool first_tile = true;
+    // per-lane accumulators of the SIMT-side gradients: this lane's column of db2/db1/db0 (16 columns of this half),
+    // of dW3 (16 columns) and db3
+    float acc_db2 = 0.f, acc_db1 = 0.f, acc_db0 = 0.f, acc_dw3 = 0.f, acc_db3 = 0.f;
+
+    auto sync_issue = [&]() {
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+    };
+    auto wait_mma = [&]() {
+        umma::mbar_wait(&ctl->mbar, phase);
+        phase ^= 1;
+        umma::fence_after_sync();
+    };
+    auto desc = [&](uint32_t base, uint32_t chunk, uint32_t lbo, uint32_t sbo) { return umma::make_desc(base + chunk * LBO, lbo, sbo); };
+
+    const uint64_t n_tiles = (P + TILE - 1) / TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t p = tile * TILE + r;
+        const bool valid = p < P;
+        float x[3] = {0.f, 0.f, 0.f};
+        float dsig = 0.f;
+        if (valid) {
+            fetch_point<SRC>(sp, p, x);
+            if constexpr (SRC == NAFB_SRC_RAYS) {
+                const uint32_t ray = (uint32_t)(p / sp.n_samples);
+                const uint32_t i = (uint32_t)(p - (uint64_t)ray * sp.n_samples);
+                const RayRegs R = load_ray(sp.rays, ray);
+                dsig = __fmul_rn(__ldg(dsig_or_dacc + ray), ray_delta(sp, R, ray, i));
+            } else {
+                dsig = __ldg(dsig_or_dacc + p);
+            }
+        }
+        float x01[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x01[d] = normalise01(x[d], sp.bound, sp.inv_2bound);
+        {
+            float enc[16];
+            gather_half<C>(gp, x01, half, enc);
+            store_half_row(A_hi, A_lo, r, CH_ENC, half, BX_SBO, enc);
+        }
+        float v[16];
+        // ---------------- forward layer 0
+        sync_issue();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_ENC, LBO, BX_SBO), desc(a_lo, CH_ENC, LBO, BX_SBO),
+                             umma::make_desc(w_hi + W0_OFF, LBO, W0_SBO), umma::make_desc(w_lo + W0_OFF, LBO, W0_SBO), 256, 256, 2, ID_FWD, false);
+            umma::commit(&ctl->mbar);
+        }
+        wait_mma();
+        umma::tmem_ld16(taddr + T_S, v);
+        umma::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = leaky_relu(v[i] + small->b0[16 * half + i]);
+        store_half_row(A_hi, A_lo, r, CH_H0, half, BX_SBO, v);
+        // ---------------- forward layer 1
+        sync_issue();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_H0, LBO, BX_SBO), desc(a_lo, CH_H0, LBO, BX_SBO),
+                             umma::make_desc(w_hi + W1_OFF, LBO, W1_SBO), umma::make_desc(w_lo + W1_OFF, LBO, W1_SBO), 256, 256, 2, ID_FWD, false);
+            umma::commit(&ctl->mbar);
+        }
+        wait_mma();
+        umma::tmem_ld16(taddr + T_S, v);
+        umma::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = leaky_relu(v[i] + small->b1[16 * half + i]);
+        store_half_row(A_hi, A_lo, r, CH_H1, half, BX_SBO, v);
+        // ---------------- forward layer 2: [enc | h1] (chunks 4..11) . W2^T
+        sync_issue();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_ENC, LBO, BX_SBO), desc(a_lo, CH_ENC, LBO, BX_SBO),
+                             umma::make_desc(w_hi + W2_OFF, LBO, W2_SBO), umma::make_desc(w_lo + W2_OFF, LBO, W2_SBO), 256, 256, 4, ID_FWD, false);
+            umma::commit(&ctl->mbar);
+        }
+        wait_mma();
+        umma::tmem_ld16(taddr + T_S, v);
+        umma::tmem_wait_ld();
+        // ---------------- head forward + backward (fp32 SIMT)
+        float h2[16];
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            h2[i] = leaky_relu(v[i] + small->b2[16 * half + i]);
+            part = __fmaf_rn(h2[i], small->w3[16 * half + i], part);
+        }
+        if (half == 1) xchg[r] = part;
+        __syncthreads();
+        if (half == 0) {
+            const float s = (part + xchg[r]) + small->b3;
+            const float y = head_activation(s, mp.head);
+            xchg2[r] = dsig * head_derivative(s, y, mp.head);
+        }
+        __syncthreads();
+        const float gpre = xchg2[r];
+        {
+            float gw3[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                gw3[i] = gpre * h2[i];                                                          // dW3 contribution
+                v[i] = __fmul_rn(__fmul_rn(small->w3[16 * half + i], gpre), h2[i] > 0.f ? 1.0f : 0.01f);  // dz2
+            }
+            acc_dw3 += warp_colsum16(gw3, lane);
+            acc_db2 += warp_colsum16(v, lane);
+            if (half == 0) acc_db3 += warp_sum(gpre);
+        }
+        store_half_row(A_hi, A_lo, r, CH_G, half, BX_SBO, v);
+        // ---------------- backward layer 2: dW2 += G^T.[enc|h1];  d_enc = G.W2[:, :32];  dh1 = G.W2[:, 32:]
+        sync_issue();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem + T_DW2, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_ENC, BX_SBO, LBO),
+                             desc(a_lo, CH_ENC, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW64, !first_tile);
+            umma::mma_bf16x3(tmem + T_DENC, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
+                             umma::make_desc(w_hi + W2_OFF, W2_SBO, LBO), umma::make_desc(w_lo + W2_OFF, W2_SBO, LBO), 256, 2 * W2_SBO, 2, ID_DX, false);
+            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
+                             umma::make_desc(w_hi + W2_OFF + 4 * LBO, W2_SBO, LBO), umma::make_desc(w_lo + W2_OFF + 4 * LBO, W2_SBO, LBO), 256,
+                             2 * W2_SBO, 2, ID_DX, false);
+            umma::commit(&ctl->mbar);
+        }
+        wait_mma();
+        umma::tmem_ld16(taddr + T_S, v);
+        umma::tmem_wait_ld();
+        {
+            float s[16];
+            lrelu_slopes(A_hi, r, CH_H1, half, BX_SBO, s);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], s[i]);  // dz1
+            acc_db1 += warp_colsum16(v, lane);
+        }
+        store_half_row(A_hi, A_lo, r, CH_G, half, BX_SBO, v);
+        // ---------------- backward layer 1: dW1 += G^T.h0;  dh0 = G.W1
+        sync_issue();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem + T_DW1, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_H0, BX_SBO, LBO),
+                             desc(a_lo, CH_H0, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW32, !first_tile);
+            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
+                             umma::make_desc(w_hi + W1_OFF, W1_SBO, LBO), umma::make_desc(w_lo + W1_OFF, W1_SBO, LBO), 256, 2 * W1_SBO, 2, ID_DX, false);
+            umma::commit(&ctl->mbar);
+        }
+        wait_mma();
+        umma::tmem_ld16(taddr + T_S, v);
+        umma::tmem_wait_ld();
+        {
+            float s[16];
+            lrelu_slopes(A_hi, r, CH_H0, half, BX_SBO, s);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], s[i]);  // dz0
+            acc_db0 += warp_colsum16(v, lane);
+        }
+        store_half_row(A_hi, A_lo, r, CH_G, half, BX_SBO, v);
+        // ---------------- backward layer 0: dW0 += G^T.enc;  d_enc += G.W0
+        sync_issue();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::mma_bf16x3(tmem + T_DW0, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_ENC, BX_SBO, LBO),
+                             desc(a_lo, CH_ENC, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW32, !first_tile);
+            umma::mma_bf16x3(tmem + T_DENC, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
+                             umma::make_desc(w_hi + W0_OFF, W0_SBO, LBO), umma::make_desc(w_lo + W0_OFF, W0_SBO, LBO), 256, 2 * W0_SBO, 2, ID_DX, true);
+            umma::commit(&ctl->mbar);
+        }
+        wait_mma();
+        umma::tmem_ld16(taddr + T_DENC, v);
+        umma::tmem_wait_ld();
+        umma::fence_before_sync();
+        // ---------------- scatter d(encoding) into the gradient table
+        if (valid && grad_table) scatter_half<C>(gp, x01, half, v, grad_table);
+        first_tile = false;
+        __syncthreads();
+    }
+
+    // ================= flush the MLP gradients of this CTA into its slot of the partials workspace
+    float *mine = partials + (size_t)blockIdx.x * PTOTAL;
+    const bool did_work = blockIdx.x < n_tiles;
+    // SIMT-side sums: every warp holds partial column sums over its 32 rows; combine the 4 warps of each half
+    wred[warp * 80 + 0 * 16 + colsum_index(lane)] = acc_db2;   // lanes l and l^1 hold the same column: benign duplicate store
+    wred[warp * 80 + 1 * 16 + colsum_index(lane)] = acc_db1;
+    wred[warp * 80 + 2 * 16 + colsum_index(lane)] = acc_db0;
+    wred[warp * 80 + 3 * 16 + colsum_index(lane)] = acc_dw3;
+    if (lane == 0) wred[warp * 80 + 64] = acc_db3;
+    __syncthreads();
+    if (t < 32) {   // column j of the 32-wide vectors: half = j / 16 -> warps 4*half .. 4*half+3
+        const int hj = t >> 4, cj = t & 15;
+        float s2 = 0.f, s1 = 0.f, s0 = 0.f, sw = 0.f;
+        for (int w = 0; w < 4; ++w) {
+            const float *q = wred + (4 * hj + w) * 80;
+            s2 += q[0 * 16 + cj]; s1 += q[1 * 16 + cj]; s0 += q[2 * 16 + cj]; sw += q[3 * 16 + cj];
+        }
+        mine[PB2 + t] = s2; mine[PB1 + t] = s1; mine[PB0 + t] = s0; mine[PW3 + t] = sw;
+        if (t == 0) {
+            float s3 = 0.f;
+            for (int w = 0; w < 4; ++w) s3 += wred[w * 80 + 64];
+            mine[PB3] = s3;
+            mine[PB3 + 1] = mine[PB3 + 2] = mine[PB3 + 3] = 0.f;
+        }
+    }
+    // tensor-core side: dW_l[o][k] sits in TMEM lane o (0..31) -> warps 0 and 4 read it (16 columns at a time)
+    if ((warp & 3) == 0) {
+        float w16[16];
+        auto dump = [&](uint32_t tcol, int dst, int ldw, int ncols) {
+            for (int c0 = 16 * half; c0 < ncols; c0 += 32) {
+                if (did_work) {
+                    umma::tmem_ld16(tmem + tcol + c0, w16);   // lanes 0..31 of quadrant 0
+                    umma::tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w16[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) mine[dst + lane * ldw + c0 + i] = w16[i];
+            }
+        };
+        dump(T_DW0, PW0, 32, 32);
+        dump(T_DW1, PW1, 32, 32);
+        dump(T_DW2, PW2, 64, 64);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, T_COLS);
+}
+
+bool tc_config_ok(const nafb_grid *grid, const nafb_mlp *mlp) {
+    return grid->D == 3 && grid->L * grid->C == 32 && mlp->in_dim == 32 && mlp->hidden == 32 && mlp->out_dim == 1 && mlp->n_layers == 4 &&
+           mlp->skip_mask == (1u << 2);
+}
+
+template <int SRC, int C>
+int launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, float *sigma, float *acc, float *z, float *pts,
+                  int32_t *flags, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_density_fwd_tc<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
+        if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_forward(tc): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const uint64_t n_tiles = (P + TILE - 1) / TILE;
+    const uint64_t cap = (uint64_t)nafb_sm_count() * 3;
+    const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+    k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags);
+    NAFB_CHECK_LAUNCH("density_forward(tc)");
+    return NAFB_OK;
+}
+
+}  // namespace
+
+// ---- entry points used by density.cu's dispatcher
+bool nafb_tc_config_ok(const nafb_grid *grid, const nafb_mlp *mlp) { return tc_config_ok(grid, mlp); }
+
+int nafb_tc_bwd_grid(uint64_t n_tiles) {
+    const uint64_t cap = (uint64_t)nafb_sm_count() * 2;
+    return (int)(n_tiles < cap ? n_tiles : cap);
+}
+
+int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
+                       float *pts, int32_t *flags, cudaStream_t s) {
+#define CALL(S_, C_) launch_fwd_tc<S_, C_>(gp, mp, sp, P, sigma, acc, z, pts, flags, s)
+    switch (gp.C) {
+        case 1: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 1) : src == NAFB_SRC_RAYS ? CALL(NAFB_SRC_RAYS, 1) : CALL(NAFB_SRC_VOXELS, 1);
+        case 2: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 2) : src == NAFB_SRC_RAYS ? CALL(NAFB_SRC_RAYS, 2) : CALL(NAFB_SRC_VOXELS, 2);
+        case 4: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 4) : src == NAFB_SRC_RAYS ? CALL(NAFB_SRC_RAYS, 4) : CALL(NAFB_SRC_VOXELS, 4);
+        default: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 8) : src == NAFB_SRC_RAYS ? CALL(NAFB_SRC_RAYS, 8) : CALL(NAFB_SRC_VOXELS, 8);
+    }
+#undef CALL
+}
+
+template <int SRC, int C>
+static int launch_bwd_tc_t(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, const float *dsig, float *grad_table,
+                           float *partials, int grid, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_density_bwd_tc<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
+        if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    k_density_bwd_tc<SRC, C><<<grid, NT, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials);
+    NAFB_CHECK_LAUNCH("density_backward(tc)");
+    return NAFB_OK;
+}
+
+int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
+                       float *grad_table, float *partials, int grid, cudaStream_t s) {
+#define CALL(S_, C_) launch_bwd_tc_t<S_, C_>(gp, mp, sp, P, dsig, grad_table, partials, grid, s)
+    switch (gp.C) {
+        case 1: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 1) : CALL(NAFB_SRC_RAYS, 1);
+        case 2: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 2) : CALL(NAFB_SRC_RAYS, 2);
+        case 4: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 4) : CALL(NAFB_SRC_RAYS, 4);
+        default: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 8) : CALL(NAFB_SRC_RAYS, 8);
+    }
+#undef CALL
+}

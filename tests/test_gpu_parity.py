@@ -31,6 +31,18 @@ from oracle import naf
 
 DEV = "cuda"
 
+# Arithmetic of the fused density kernels: 0 = tcgen05 tensor cores (bf16x3 split operands, fp32 accumulation
+# in TMEM; the default), 1 = fp32 SIMT FMAs.  Every density / render / engine test runs in both modes.
+both_modes = pytest.mark.parametrize("mlp_mode", [0, 1], ids=["tcgen05", "simt"], indirect=True)
+
+
+@pytest.fixture
+def mlp_mode(request):
+    mode = request.param if hasattr(request, "param") else 0
+    _lib.check(_lib.lib().nafb_set_mlp_mode(mode))
+    yield mode
+    _lib.check(_lib.lib().nafb_set_mlp_mode(0))
+
 
 def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
@@ -211,8 +223,9 @@ def _oracle_net(net, normalise="mul_recip"):
     return o
 
 
+@both_modes
 @pytest.mark.parametrize("head", ["sigmoid", "relu", "tanh", "none"])
-def test_density_forward_golden(golden, head):
+def test_density_forward_golden(golden, head, mlp_mode):
     fx = golden("render.npz")
     net = _chest_net(last_activation=head)
     _load_mlp(net, fx, "chest_")
@@ -223,7 +236,8 @@ def test_density_forward_golden(golden, head):
     np.testing.assert_allclose(s, fx[key], rtol=2e-5, atol=2e-6)
 
 
-def test_density_deep_two_skips(golden):
+@both_modes
+def test_density_deep_two_skips(golden, mlp_mode):
     fx = golden("render.npz")
     net = _chest_net(num_layers=6, skips=[2, 4])
     _load_mlp(net, fx, "deep_")
@@ -233,7 +247,8 @@ def test_density_deep_two_skips(golden):
     np.testing.assert_allclose(s, fx["deep_sigma"], rtol=2e-5, atol=2e-6)
 
 
-def test_density_fused_vs_unfused_and_oracle():
+@both_modes
+def test_density_fused_vs_unfused_and_oracle(mlp_mode):
     torch.manual_seed(1)
     net = _chest_net(table_scale=0.3)
     pts = ((torch.rand(5000, 3, device=DEV) * 2 - 1) * 0.29)
@@ -256,7 +271,8 @@ def test_density_fused_vs_unfused_and_oracle():
         np.testing.assert_allclose(a.cpu().numpy(), b.grad.numpy(), rtol=2e-3, atol=2e-5)
 
 
-def test_density_ragged_and_range():
+@both_modes
+def test_density_ragged_and_range(mlp_mode):
     net = _chest_net()
     for P in [1, 127, 128, 129, 1000]:
         pts = (torch.rand(P, 3, device=DEV) * 2 - 1) * 0.3
@@ -268,7 +284,8 @@ def test_density_ragged_and_range():
 
 
 # ----------------------------------------------------------------------------- render
-def test_render_golden_chest(golden):
+@both_modes
+def test_render_golden_chest(golden, mlp_mode):
     fx = golden("render.npz")
     net = _chest_net()
     _load_mlp(net, fx, "chest_")
@@ -322,7 +339,8 @@ def test_render_unfused_pieces_golden(golden):
     np.testing.assert_allclose(rc["acc"].detach().cpu().numpy(), fx["freq_acc_noperturb"], rtol=1e-4, atol=1e-7)
 
 
-def test_render_vs_oracle_full_shape():
+@both_modes
+def test_render_vs_oracle_full_shape(mlp_mode):
     """chest_50 shape (1024 rays x 192 samples): forward + gradients against the CPU oracle."""
     torch.manual_seed(5)
     rng = np.random.default_rng(5)
@@ -366,7 +384,8 @@ def test_mse_loss_chunks_and_mask(golden):
 
 
 # ----------------------------------------------------------------------------- voxel query + engine
-def test_voxel_query_vs_oracle():
+@both_modes
+def test_voxel_query_vs_oracle(mlp_mode):
     net = _chest_net(table_scale=0.3)
     eng = NAFEngine(net, n_samples=8, use_cuda_graph=False)
     geo = naf.Geometry(dict(DSD=1500.0, DSO=1000.0, nDetector=[8, 8], dDetector=[1.0, 1.0], nVoxel=[20, 17, 9], dVoxel=[1.0, 2.0, 3.0],
@@ -412,7 +431,8 @@ def test_adam_matches_torch():
     print("adam bit-exact vs torch.optim.Adam:", exact)
 
 
-def test_engine_train_steps_vs_oracle():
+@both_modes
+def test_engine_train_steps_vs_oracle(mlp_mode):
     """Five fused steps (graph replay) track five oracle steps (CPU autograd + torch Adam)."""
     rng = np.random.default_rng(9)
     N, S = 256, 64
