@@ -367,7 +367,15 @@ def test_render_vs_oracle_full_shape(mlp_mode):
     for a, b in zip(net.parameters(), o.parameters()):
         ga, gb = a.grad.cpu().numpy(), b.grad.numpy()
         scale = np.abs(gb).max()
-        np.testing.assert_allclose(ga, gb, rtol=5e-3, atol=2e-5 * scale)
+        if mlp_mode == 1:
+            np.testing.assert_allclose(ga, gb, rtol=5e-3, atol=2e-5 * scale)
+        else:
+            # mixed-precision tolerance (bf16x3 operands): a hidden unit within ~1e-5 of zero can take the other
+            # LeakyReLU slope, which changes the gradient footprint of that one sample point (128 table entries).
+            # Require: relative L2 error < 2e-4 and at most 1e-5 of the elements outside the fp32 tolerance.
+            bad = ~np.isclose(ga, gb, rtol=5e-3, atol=2e-5 * scale)
+            assert bad.mean() < 1e-5, bad.sum()
+            assert np.linalg.norm((ga - gb).ravel()) / np.linalg.norm(gb.ravel()) < 2e-4
 
 
 def test_mse_loss_chunks_and_mask(golden):
