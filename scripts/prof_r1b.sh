@@ -1,0 +1,9 @@
+set -x
+CMD="python bench.py --steps 6 --warmup 3 --no-cpu-baseline --profile-steps 3"
+timeout 300 $CMD > gpurun_out/prof_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_density_bwd_tc -s 2 -c 1 -o gpurun_out/r1b_density_bwd_tc $CMD > gpurun_out/ncu_full.log 2>&1
+echo "full exit $?"
+ncu --set full --clock-control none --import-source on -k regex:k_density_fwd_tc -s 2 -c 1 -o gpurun_out/r1b_density_fwd_tc $CMD > gpurun_out/ncu_full2.log 2>&1
+echo "full2 exit $?"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_density|k_adam|k_mse|k_reduce" -c 60 --csv --log-file gpurun_out/r1b_launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+echo "launch-list exit $?"
