@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -12,6 +13,15 @@ void nafb_set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+int nafb_debug_flags() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("NAFB_DEBUG_SKIP");
+        cached = e ? atoi(e) : 0;
+    }
+    return cached;
 }
 
 int nafb_sm_count() {

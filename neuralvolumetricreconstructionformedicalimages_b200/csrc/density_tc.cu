@@ -18,6 +18,10 @@
 #include "sampler.cuh"
 #include "umma.cuh"
 
+// profiling knobs (env NAFB_DEBUG_SKIP, read once): bit 0 = skip the gradient scatter, bit 1 = skip the table
+// gather (synthetic encodings).  Results are wrong with any bit set; used only to attribute kernel time.
+int nafb_debug_flags();
+
 namespace {
 
 constexpr int TILE = 128;
@@ -200,7 +204,7 @@ constexpr uint32_t FWD_SMEM = 2 * FX_HALF + 2 * W_HALF + sizeof(SmallParams) + s
 template <int SRC, int C>
 __global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           float *__restrict__ sigma, float *__restrict__ acc_out, float *__restrict__ z_out,
-                                                          float *__restrict__ pts_out, int32_t *__restrict__ flags) {
+                                                          float *__restrict__ pts_out, int32_t *__restrict__ flags, const int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *X_hi = smem, *X_lo = X_hi + FX_HALF;
     uint8_t *W_hi = X_lo + FX_HALF, *W_lo = W_hi + W_HALF;
@@ -245,7 +249,12 @@ __global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, c
         for (int d = 0; d < 3; ++d) x01[d] = normalise01(x[d], sp.bound, sp.inv_2bound);
         {
             float enc[16];
-            gather_half<C>(gp, x01, half, enc);
+            if (dbg & 2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) enc[i] = x01[i % 3];
+            } else {
+                gather_half<C>(gp, x01, half, enc);
+            }
             store_half_row(X_hi, X_lo, r, 0, half, FX_SBO, enc);
         }
         // ---------------- layer 0: enc . W0^T
@@ -363,7 +372,7 @@ constexpr int PW0 = 0, PW1 = 1024, PW2 = 2048, PW3 = 4096, PB0 = 4128, PB1 = 416
 template <int SRC, int C>
 __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           const float *__restrict__ dsig_or_dacc, float *__restrict__ grad_table,
-                                                          float *__restrict__ partials) {
+                                                          float *__restrict__ partials, const int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *A_hi = smem, *A_lo = A_hi + BX_HALF;
     uint8_t *W_hi = A_lo + BX_HALF, *W_lo = W_hi + W_HALF;
@@ -435,7 +444,12 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         for (int d = 0; d < 3; ++d) x01[d] = normalise01(x[d], sp.bound, sp.inv_2bound);
         {
             float enc[16];
-            gather_half<C>(gp, x01, half, enc);
+            if (dbg & 2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) enc[i] = x01[i % 3];
+            } else {
+                gather_half<C>(gp, x01, half, enc);
+            }
             store_half_row(A_hi, A_lo, r, CH_ENC, half, BX_SBO, enc);
         }
         float v[16];
@@ -567,7 +581,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         umma::tmem_wait_ld();
         umma::fence_before_sync();
         // ---------------- scatter d(encoding) into the gradient table
-        if (valid && grad_table) scatter_half<C>(gp, x01, half, v, grad_table);
+        if (valid && grad_table && !(dbg & 1)) scatter_half<C>(gp, x01, half, v, grad_table);
         first_tile = false;
         __syncthreads();
     }
@@ -639,7 +653,7 @@ int launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams 
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
     const uint64_t cap = (uint64_t)nafb_sm_count() * 3;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags);
+    k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags, nafb_debug_flags());
     NAFB_CHECK_LAUNCH("density_forward(tc)");
     return NAFB_OK;
 }
@@ -675,7 +689,7 @@ static int launch_bwd_tc_t(const GridParams &gp, const nafb_mlp &mp, const Sampl
         if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): %s", cudaGetErrorString(e));
         configured = true;
     }
-    k_density_bwd_tc<SRC, C><<<grid, NT, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials);
+    k_density_bwd_tc<SRC, C><<<grid, NT, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, nafb_debug_flags());
     NAFB_CHECK_LAUNCH("density_backward(tc)");
     return NAFB_OK;
 }
