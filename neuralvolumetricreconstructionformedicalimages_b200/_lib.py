@@ -63,6 +63,7 @@ _SIGNATURES = {
     "nafb_ray_integral_backward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_mse_loss": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, u32, u32, ctypes.c_float, c_f32p, c_f32p, ctypes.c_void_p]),
     "nafb_set_mlp_mode": (ctypes.c_int, [ctypes.c_int]),
+    "nafb_microbench": (ctypes.c_int, [ctypes.c_int, c_f32p, u32, ctypes.c_int, c_f32p, ctypes.POINTER(u64), ctypes.c_void_p]),
     "nafb_selftest_umma": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_void_p]),
     "nafb_adam_step": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, u32, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
 }
