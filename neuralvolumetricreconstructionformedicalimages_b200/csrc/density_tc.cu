@@ -96,11 +96,14 @@ __device__ __forceinline__ void gather_half(const GridParams &gp, const float (&
 }
 
 template <int C>
-__device__ __forceinline__ void scatter_half(const GridParams &gp, const float (&x01)[3], int half, const float (&genc)[16], float *grad_table) {
+__device__ __forceinline__ void scatter_half(const GridParams &gp, const float (&x01)[3], int half, const float (&genc)[16], float *grad_table,
+                                             int dbg = 0) {
     constexpr int LH = 16 / C;
 #pragma unroll
     for (int li = 0; li < LH; ++li) {
         const int l = half * LH + li;
+        if ((dbg & 4) && l < 6) continue;
+        if ((dbg & 8) && l >= 6) continue;
         const LevelParams lp = gp.lv[l];
         float *tab = grad_table + (size_t)lp.offset * C;
         uint32_t g[3];
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         umma::tmem_wait_ld();
         umma::fence_before_sync();
         // ---------------- scatter d(encoding) into the gradient table
-        if (valid && grad_table && !(dbg & 1)) scatter_half<C>(gp, x01, half, v, grad_table);
+        if (valid && grad_table && !(dbg & 1)) scatter_half<C>(gp, x01, half, v, grad_table, dbg);
         first_tile = false;
         __syncthreads();
     }
