@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 1
+#define NAFB_ABI_VERSION 2
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -122,23 +122,31 @@ typedef struct nafb_sampler {
     float clamp;             /* render.py:104: fp32(bound - 1e-6); RAYS source clamps to +-clamp */
 } nafb_sampler;
 
+/* Encoding stash (optional, training only).  A forward pass that is going to be followed by
+ * nafb_density_backward on the SAME grid / mlp / sampler may leave the encodings of its points in
+ * `stash` (nafb_density_stash_bytes() bytes of device memory, 128 B per point rounded up to 128-point
+ * tiles); the backward pass then reads them back with full-line loads instead of repeating the
+ * 8-corner gather of every level.  Returns 0 when the current arithmetic mode / configuration does
+ * not use a stash (pass NULL then; NULL is always valid and means "recompute"). */
+uint64_t nafb_density_stash_bytes(const nafb_grid *grid, const nafb_mlp *mlp, uint64_t n_points);
+
 /* sigma[P*out_dim] = DensityNetwork.forward(points)   (network.py:34-58; forward only).
  * With src == NAFB_SRC_RAYS and acc != NULL it also integrates (render.py:192-201):
- *   acc[r] = sum_i sigma[r,i] * (z[r,i+1]-z[r,i]) * |d_r|   (last delta 1e-10)
+ *   acc[r] += sum_i sigma[r,i] * (z[r,i+1]-z[r,i]) * |d_r|   (last delta 1e-10; caller pre-zeroes acc)
  * and writes z_vals [N,S] / pts [N,S,3] when those pointers are non-NULL.
  * flags[0] is OR-ed with 1 if a position leaves [-bound, bound] (hashgrid.py:122), 2 on NaN/Inf. */
 int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src,
                          float *sigma, float *acc, float *z_vals, float *pts_out, int32_t *flags,
-                         nafb_stream_t stream);
+                         void *stash, nafb_stream_t stream);
 
 /* Backward of the above.  dsigma [P] (src POINTS) or dacc [N] (src RAYS: dsigma is derived as
- * dacc[r] * delta[r,i] in-kernel).  Recomputes the forward activations (nothing but the
- * points was saved), accumulates MLP gradients and scatters into grad_table.
+ * dacc[r] * delta[r,i] in-kernel).  Recomputes the forward activations from the points (and the
+ * stash, when given), accumulates MLP gradients and scatters into grad_table.
  *   workspace: nafb_density_backward_workspace_bytes() bytes of device scratch. */
 uint64_t nafb_density_backward_workspace_bytes(const nafb_mlp *mlp);
 int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src,
                           const float *dsigma_or_dacc, float *grad_table, const nafb_mlp_grads *grads,
-                          void *workspace, nafb_stream_t stream);
+                          void *workspace, const void *stash, nafb_stream_t stream);
 
 /* ------------------------------------------------------------------ sampling / integral (unfused API)
  * nafb_sample_points: render.py:88-105 -> z_vals [N,S], pts [N,S,3]; tv_partial [N] gets

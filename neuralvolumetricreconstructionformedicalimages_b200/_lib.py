@@ -16,6 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnafb200.so")
 
+ABI_VERSION = 2
 NAFB_MAX_LEVELS = 32
 NAFB_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
@@ -55,9 +56,10 @@ _SIGNATURES = {
     "nafb_hash_encode_forward": (ctypes.c_int, [ctypes.POINTER(Grid), c_f32p, c_f32p, u32, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_void_p]),
     "nafb_hash_encode_backward": (ctypes.c_int, [ctypes.POINTER(Grid), c_f32p, c_f32p, c_f32p, u32, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p, ctypes.c_void_p]),
     "nafb_minmax": (ctypes.c_int, [c_f32p, u64, c_f32p, ctypes.c_void_p]),
-    "nafb_density_forward": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), ctypes.c_int, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nafb_density_stash_bytes": (u64, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), u64]),
+    "nafb_density_forward": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), ctypes.c_int, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nafb_density_backward_workspace_bytes": (u64, [ctypes.POINTER(Mlp)]),
-    "nafb_density_backward": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), ctypes.c_int, c_f32p, c_f32p, ctypes.POINTER(MlpGrads), ctypes.c_void_p, ctypes.c_void_p]),
+    "nafb_density_backward": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), ctypes.c_int, c_f32p, c_f32p, ctypes.POINTER(MlpGrads), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nafb_sample_points": (ctypes.c_int, [ctypes.POINTER(Sampler), c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
     "nafb_ray_integral_forward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_ray_integral_backward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
@@ -93,7 +95,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.nafb_abi_version() != 1:
+        if L.nafb_abi_version() != ABI_VERSION:
             raise RuntimeError("libnafb200.so ABI version mismatch; rebuild the extension")
         _lib = L
     return _lib

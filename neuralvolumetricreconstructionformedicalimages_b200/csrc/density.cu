@@ -22,10 +22,11 @@
 // tcgen05 edition (density_tc.cu)
 bool nafb_tc_config_ok(const nafb_grid *grid, const nafb_mlp *mlp);
 int nafb_tc_bwd_grid(uint64_t n_tiles);
+uint64_t nafb_tc_stash_bytes(uint64_t n_points);
 int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
-                       float *pts, int32_t *flags, cudaStream_t s);
+                       float *pts, int32_t *flags, void *stash, cudaStream_t s);
 int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
-                       float *grad_table, float *partials, int grid, cudaStream_t s);
+                       float *grad_table, float *partials, const void *stash, int grid, cudaStream_t s);
 static int g_mlp_mode = 0;  // 0: tensor cores when the configuration allows, 1: fp32 SIMT everywhere
 
 namespace {
@@ -568,8 +569,13 @@ int launch_bwd(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp
 
 extern "C" {
 
+uint64_t nafb_density_stash_bytes(const nafb_grid *grid, const nafb_mlp *mlp, uint64_t n_points) {
+    if (!grid || !mlp || g_mlp_mode != 0 || !nafb_tc_config_ok(grid, mlp)) return 0;
+    return nafb_tc_stash_bytes(n_points);
+}
+
 int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src, float *sigma, float *acc,
-                         float *z_vals, float *pts_out, int32_t *flags, nafb_stream_t stream) {
+                         float *z_vals, float *pts_out, int32_t *flags, void *stash, nafb_stream_t stream) {
     GridParams gp;
     int rc = nafb_make_grid_params(grid, &gp);
     if (rc) return rc;
@@ -580,7 +586,7 @@ int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_
     if (P == 0) return NAFB_OK;
     if (src != NAFB_SRC_RAYS && (acc || z_vals || pts_out)) NAFB_FAIL(NAFB_ERR_INVALID, "density_forward: acc/z_vals/pts_out need the RAYS source");
     cudaStream_t s = (cudaStream_t)stream;
-    if (g_mlp_mode == 0 && nafb_tc_config_ok(grid, mlp)) return nafb_launch_fwd_tc(gp, *mlp, sp, src, P, sigma, acc, z_vals, pts_out, flags, s);
+    if (g_mlp_mode == 0 && nafb_tc_config_ok(grid, mlp)) return nafb_launch_fwd_tc(gp, *mlp, sp, src, P, sigma, acc, z_vals, pts_out, flags, stash, s);
 #define CALL(S_, C_) launch_fwd<S_, C_>(gp, *mlp, sp, P, sigma, acc, z_vals, pts_out, flags, s)
     DISPATCH_SRC_C(src, gp.C, CALL);
 #undef CALL
@@ -599,7 +605,7 @@ uint64_t nafb_density_backward_workspace_bytes(const nafb_mlp *mlp) {
 }
 
 int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src, const float *dsigma_or_dacc,
-                          float *grad_table, const nafb_mlp_grads *grads, void *workspace, nafb_stream_t stream) {
+                          float *grad_table, const nafb_mlp_grads *grads, void *workspace, const void *stash, nafb_stream_t stream) {
     GridParams gp;
     int rc = nafb_make_grid_params(grid, &gp);
     if (rc) return rc;
@@ -613,7 +619,7 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
     cudaStream_t s = (cudaStream_t)stream;
     if (g_mlp_mode == 0 && nafb_tc_config_ok(grid, mlp)) {
         const int grid_tc = nafb_tc_bwd_grid((P + TILE - 1) / TILE);
-        if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, grid_tc, s))) return rc;
+        if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, grid_tc, s))) return rc;
         const MlpLayout lo = make_layout(*mlp);
         k_reduce_partials<<<(lo.total + 255) / 256, 256, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
         NAFB_CHECK_LAUNCH("density_backward(reduce)");

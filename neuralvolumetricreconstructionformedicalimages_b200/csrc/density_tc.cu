@@ -95,30 +95,86 @@ __device__ __forceinline__ void gather_half(const GridParams &gp, const float (&
     }
 }
 
+// Gradient scatter of one point.  `genc` holds all 32 columns of d(encoding) of the point; the thread
+// scatters levels l = 2*li + half (even levels on half 0, odd on half 1: the contended coarse levels
+// and the all-miss fine levels are split evenly over the two halves of the CTA).
+//
+// Coarse levels are WARP-AGGREGATED: the 32 lanes of a warp hold 32 consecutive sample points (for the
+// ray source: consecutive samples of one ray), which fall into a few grid cells only.  Lanes of one
+// cell form a contiguous run; a segmented suffix sum over the run (5 shuffle steps per value) leaves
+// the run totals of the 8 corners x C channels in the run's first lane, which issues the only
+// reductions of the run.  The L2 atomic unit serialises per address (and the few hot lines of a coarse
+// level live in a handful of L2 slices), so the number of reductions -- not their bytes -- is what the
+// backward pass pays for.  The choice is made per warp and level from the number of runs (ballot).
+constexpr int AGG_LI = 4;          // levels 0 .. 2*AGG_LI-1 may be aggregated
+constexpr int AGG_MAX_RUNS = 20;   // aggregate when the warp has at most this many runs
+
 template <int C>
-__device__ __forceinline__ void scatter_half(const GridParams &gp, const float (&x01)[3], int half, const float (&genc)[16], float *grad_table,
-                                             int dbg = 0) {
-    constexpr int LH = 16 / C;
+__device__ __forceinline__ void scatter_levels(const GridParams &gp, const float (&x01)[3], const int half, const bool valid, const unsigned lane,
+                                               const float (&genc)[32], float *grad_table, const int dbg) {
+    constexpr int NL = 32 / C;  // levels of the grid
 #pragma unroll
-    for (int li = 0; li < LH; ++li) {
-        const int l = half * LH + li;
+    for (int li = 0; li < NL / 2; ++li) {
+        const int l = 2 * li + half;
         if ((dbg & 4) && l < 6) continue;
         if ((dbg & 8) && l >= 6) continue;
         const LevelParams lp = gp.lv[l];
         float *tab = grad_table + (size_t)lp.offset * C;
+        float ge[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ge[c] = half ? genc[(2 * li + 1) * C + c] : genc[(2 * li) * C + c];
         uint32_t g[3];
         float f[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
+        bool direct = true;
+        if (li < AGG_LI && !(dbg & 16)) {
+            // runs of equal cells among consecutive lanes (invalid lanes: a run of their own, never issued)
+            const uint32_t k0 = valid ? (g[0] | (g[1] << 16)) : 0xffffffffu, k1 = valid ? g[2] : 0xffffffffu;
+            const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
+            const bool head = lane == 0 || p0 != k0 || p1 != k1;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (__popc(heads) <= AGG_MAX_RUNS) {
+                direct = false;
+                float v[8][C];
 #pragma unroll
-        for (uint32_t idx = 0; idx < 8; ++idx) {
-            float w = 1.0f;
+                for (uint32_t idx = 0; idx < 8; ++idx) {
+                    float w = 1.0f;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
-            float v[C];
+                    for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
 #pragma unroll
-            for (int c = 0; c < C; ++c) v[c] = __fmul_rn(w, genc[li * C + c]);
-            red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v);
+                    for (int c = 0; c < C; ++c) v[idx][c] = valid ? __fmul_rn(w, ge[c]) : 0.f;
+                }
+                const uint32_t above = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));  // bit j: lane+1+j starts a new run
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const bool same = (lane + o < 32) && ((above & ((1u << o) - 1u)) == 0u);
+#pragma unroll
+                    for (uint32_t idx = 0; idx < 8; ++idx)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float up = __shfl_down_sync(0xffffffffu, v[idx][c], o);
+                            if (same) v[idx][c] += up;
+                        }
+                }
+                if (head && valid) {
+#pragma unroll
+                    for (uint32_t idx = 0; idx < 8; ++idx)
+                        red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v[idx]);
+                }
+            }
+        }
+        if (direct && valid) {
+#pragma unroll
+            for (uint32_t idx = 0; idx < 8; ++idx) {
+                float w = 1.0f;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
+                float v[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[c] = __fmul_rn(w, ge[c]);
+                red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v);
+            }
         }
     }
 }
@@ -127,6 +183,42 @@ __device__ __forceinline__ void scatter_half(const GridParams &gp, const float (
 __device__ __forceinline__ void store_half_row(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo, const float (&v)[16]) {
     umma::store_chunk_split(hi, lo, umma::canon_off(row, chunk0 + 2 * half, LBO, sbo), v);
     umma::store_chunk_split(hi, lo, umma::canon_off(row, chunk0 + 2 * half + 1, LBO, sbo), v + 8);
+}
+
+// ---- encoding stash: what a training forward leaves for the backward pass (16 KB per 128-point tile):
+// the bf16 (hi | lo) images of the tile's encodings in the canonical layout with 4 chunks per row
+// (SBO 512), i.e. byte-for-byte what the tensor core consumed.  A warp writes / reads whole 128-byte
+// lines; the backward pass then needs no table gather at all.
+constexpr uint32_t ST_SBO = 512, ST_HALF = 8192, ST_TILE = 16384;
+
+__device__ __forceinline__ void store_half_row_and_stash(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo,
+                                                         const float (&v)[16], uint8_t *stash_tile) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint4 h, l;
+        umma::split_chunk(v + 8 * c, h, l);
+        const uint32_t off = umma::canon_off(row, chunk0 + 2 * half + c, LBO, sbo);
+        *reinterpret_cast<uint4 *>(hi + off) = h;
+        *reinterpret_cast<uint4 *>(lo + off) = l;
+        if (stash_tile) {
+            const uint32_t so = umma::canon_off(row, 2 * half + c, LBO, ST_SBO);
+            *reinterpret_cast<uint4 *>(stash_tile + so) = h;   // default policy: the backward pass finds it in L2
+            *reinterpret_cast<uint4 *>(stash_tile + ST_HALF + so) = l;
+        }
+    }
+}
+
+__device__ __forceinline__ void load_stash_half_row(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo,
+                                                    const uint8_t *stash_tile) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t so = umma::canon_off(row, 2 * half + c, LBO, ST_SBO);
+        const uint4 h = __ldcs(reinterpret_cast<const uint4 *>(stash_tile + so));
+        const uint4 l = __ldcs(reinterpret_cast<const uint4 *>(stash_tile + ST_HALF + so));
+        const uint32_t off = umma::canon_off(row, chunk0 + 2 * half + c, LBO, sbo);
+        *reinterpret_cast<uint4 *>(hi + off) = h;
+        *reinterpret_cast<uint4 *>(lo + off) = l;
+    }
 }
 
 // sign of the stored activations (hi part is enough): slope of LeakyReLU at h
@@ -207,7 +299,8 @@ constexpr uint32_t FWD_SMEM = 2 * FX_HALF + 2 * W_HALF + sizeof(SmallParams) + s
 template <int SRC, int C>
 __global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           float *__restrict__ sigma, float *__restrict__ acc_out, float *__restrict__ z_out,
-                                                          float *__restrict__ pts_out, int32_t *__restrict__ flags, const int dbg) {
+                                                          float *__restrict__ pts_out, int32_t *__restrict__ flags, uint8_t *__restrict__ stash,
+                                                          const int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *X_hi = smem, *X_lo = X_hi + FX_HALF;
     uint8_t *W_hi = X_lo + FX_HALF, *W_lo = W_hi + W_HALF;
@@ -258,7 +351,7 @@ __global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, c
             } else {
                 gather_half<C>(gp, x01, half, enc);
             }
-            store_half_row(X_hi, X_lo, r, 0, half, FX_SBO, enc);
+            store_half_row_and_stash(X_hi, X_lo, r, 0, half, FX_SBO, enc, stash ? stash + tile * ST_TILE : nullptr);
         }
         // ---------------- layer 0: enc . W0^T
         umma::fence_proxy_async();
@@ -375,7 +468,7 @@ constexpr int PW0 = 0, PW1 = 1024, PW2 = 2048, PW3 = 4096, PB0 = 4128, PB1 = 416
 template <int SRC, int C>
 __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           const float *__restrict__ dsig_or_dacc, float *__restrict__ grad_table,
-                                                          float *__restrict__ partials, const int dbg) {
+                                                          float *__restrict__ partials, const uint8_t *__restrict__ stash, const int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *A_hi = smem, *A_lo = A_hi + BX_HALF;
     uint8_t *W_hi = A_lo + BX_HALF, *W_lo = W_hi + W_HALF;
@@ -445,7 +538,9 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         float x01[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) x01[d] = normalise01(x[d], sp.bound, sp.inv_2bound);
-        {
+        if (stash) {
+            load_stash_half_row(A_hi, A_lo, r, CH_ENC, half, BX_SBO, stash + tile * ST_TILE);
+        } else {
             float enc[16];
             if (dbg & 2) {
 #pragma unroll
@@ -580,11 +675,14 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             umma::commit(&ctl->mbar);
         }
         wait_mma();
-        umma::tmem_ld16(taddr + T_DENC, v);
-        umma::tmem_wait_ld();
-        umma::fence_before_sync();
-        // ---------------- scatter d(encoding) into the gradient table
-        if (valid && grad_table && !(dbg & 1)) scatter_half<C>(gp, x01, half, v, grad_table, dbg);
+        {
+            float ge[32];
+            umma::tmem_ld32(tmem + lane_base + T_DENC, ge);
+            umma::tmem_wait_ld();
+            umma::fence_before_sync();
+            // ---------------- scatter d(encoding) into the gradient table
+            if (grad_table && !(dbg & 1)) scatter_levels<C>(gp, x01, half, valid, lane, ge, grad_table, dbg);
+        }
         first_tile = false;
         __syncthreads();
     }
@@ -646,7 +744,7 @@ bool tc_config_ok(const nafb_grid *grid, const nafb_mlp *mlp) {
 
 template <int SRC, int C>
 int launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, float *sigma, float *acc, float *z, float *pts,
-                  int32_t *flags, cudaStream_t s) {
+                  int32_t *flags, uint8_t *stash, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_density_fwd_tc<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
@@ -656,7 +754,7 @@ int launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams 
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
     const uint64_t cap = (uint64_t)nafb_sm_count() * 3;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags, nafb_debug_flags());
+    k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags, stash, nafb_debug_flags());
     NAFB_CHECK_LAUNCH("density_forward(tc)");
     return NAFB_OK;
 }
@@ -671,9 +769,11 @@ int nafb_tc_bwd_grid(uint64_t n_tiles) {
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
 
+uint64_t nafb_tc_stash_bytes(uint64_t n_points) { return (n_points + TILE - 1) / TILE * (uint64_t)ST_TILE; }
+
 int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
-                       float *pts, int32_t *flags, cudaStream_t s) {
-#define CALL(S_, C_) launch_fwd_tc<S_, C_>(gp, mp, sp, P, sigma, acc, z, pts, flags, s)
+                       float *pts, int32_t *flags, void *stash, cudaStream_t s) {
+#define CALL(S_, C_) launch_fwd_tc<S_, C_>(gp, mp, sp, P, sigma, acc, z, pts, flags, (uint8_t *)stash, s)
     switch (gp.C) {
         case 1: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 1) : src == NAFB_SRC_RAYS ? CALL(NAFB_SRC_RAYS, 1) : CALL(NAFB_SRC_VOXELS, 1);
         case 2: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 2) : src == NAFB_SRC_RAYS ? CALL(NAFB_SRC_RAYS, 2) : CALL(NAFB_SRC_VOXELS, 2);
@@ -685,21 +785,21 @@ int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerPa
 
 template <int SRC, int C>
 static int launch_bwd_tc_t(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, const float *dsig, float *grad_table,
-                           float *partials, int grid, cudaStream_t s) {
+                           float *partials, const uint8_t *stash, int grid, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_density_bwd_tc<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
         if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): %s", cudaGetErrorString(e));
         configured = true;
     }
-    k_density_bwd_tc<SRC, C><<<grid, NT, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, nafb_debug_flags());
+    k_density_bwd_tc<SRC, C><<<grid, NT, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, stash, nafb_debug_flags());
     NAFB_CHECK_LAUNCH("density_backward(tc)");
     return NAFB_OK;
 }
 
 int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
-                       float *grad_table, float *partials, int grid, cudaStream_t s) {
-#define CALL(S_, C_) launch_bwd_tc_t<S_, C_>(gp, mp, sp, P, dsig, grad_table, partials, grid, s)
+                       float *grad_table, float *partials, const void *stash, int grid, cudaStream_t s) {
+#define CALL(S_, C_) launch_bwd_tc_t<S_, C_>(gp, mp, sp, P, dsig, grad_table, partials, (const uint8_t *)stash, grid, s)
     switch (gp.C) {
         case 1: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 1) : CALL(NAFB_SRC_RAYS, 1);
         case 2: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 2) : CALL(NAFB_SRC_RAYS, 2);

@@ -134,8 +134,8 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// pack 8 floats into one 16-byte chunk of the hi matrix and one of the lo matrix
-__device__ __forceinline__ void store_chunk_split(uint8_t *hi_base, uint8_t *lo_base, uint32_t off, const float *v8) {
+// 8 floats -> one 16-byte chunk of the hi matrix and one of the lo matrix
+__device__ __forceinline__ void split_chunk(const float *v8, uint4 &hi, uint4 &lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -145,8 +145,16 @@ __device__ __forceinline__ void store_chunk_split(uint8_t *hi_base, uint8_t *lo_
         h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
         l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
-    *reinterpret_cast<uint4 *>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4 *>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// pack 8 floats into one 16-byte chunk of the hi matrix and one of the lo matrix
+__device__ __forceinline__ void store_chunk_split(uint8_t *hi_base, uint8_t *lo_base, uint32_t off, const float *v8) {
+    uint4 h, l;
+    split_chunk(v8, h, l);
+    *reinterpret_cast<uint4 *>(hi_base + off) = h;
+    *reinterpret_cast<uint4 *>(lo_base + off) = l;
 }
 
 // D (+)= A*B^T over `ksteps` K-steps of 16, bf16x3: (hi,hi) + (hi,lo) + (lo,hi).

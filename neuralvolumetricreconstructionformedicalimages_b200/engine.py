@@ -27,7 +27,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .fused import density_backward, density_forward
+from .fused import density_backward, density_forward, stash_bytes
 from .network.network import DensityNetwork
 
 
@@ -79,7 +79,7 @@ class EventTimer:
 
 class NAFEngine:
     def __init__(self, net: DensityNetwork, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, n_samples=192, perturb=True, loss_chunk=None,
-                 use_cuda_graph=True, process_group=None):
+                 use_cuda_graph=True, process_group=None, use_stash=True):
         meta = net.fused_meta()
         if meta is None:
             raise RuntimeError("NAFEngine needs a DensityNetwork in a fused-capable configuration "
@@ -93,6 +93,7 @@ class NAFEngine:
         self.n_samples, self.perturb, self.loss_chunk = int(n_samples), bool(perturb), loss_chunk
         self.step_count = 0
         self.use_cuda_graph = use_cuda_graph
+        self.use_stash = bool(use_stash)  # forward leaves the encodings (128 B/point) for backward instead of a second gather
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if self.world_size > 1 else 0
@@ -125,7 +126,7 @@ class NAFEngine:
         self.grad_mlp = self._grad_views[1:]
 
     # ------------------------------------------------------------------ one training step
-    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None):
+    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None, stash=None):
         L_ = _lib.lib()
         tm = timer or _NoTimer()
         N = rays.shape[0]
@@ -138,13 +139,13 @@ class NAFEngine:
         st = _lib.stream_ptr()
         with tm("density_fwd"):
             _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, None, _lib.ptr(acc),
-                                               None, None, None, st))
+                                               None, None, None, _lib.ptr(stash), st))
         chunk = int(self.loss_chunk or 0)
         with tm("mse_loss"):
             _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), st))
         with tm("density_bwd"):
             density_backward(self.meta, self.table, self.mlp_params, dacc, self.grad_table, self.grad_mlp, rays=rays, t_rand=t_rand,
-                             n_samples=self.n_samples, perturb=self.perturb)
+                             n_samples=self.n_samples, perturb=self.perturb, stash=stash)
 
     def _adam(self, timer=None):
         L_ = _lib.lib()
@@ -172,7 +173,7 @@ class NAFEngine:
                         s["t_rand"].uniform_(0.0, 1.0)
                     else:
                         s["t_rand"].copy_(t_rand)
-            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], timer)
+            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], timer, stash=s["stash"])
             if self.world_size > 1:
                 with timer("all_reduce"):
                     dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
@@ -184,7 +185,9 @@ class NAFEngine:
         s = self._static.get(key)
         if s is None:
             d = self.device
+            nb = stash_bytes(self.meta, self.table, self.mlp_params, N * self.n_samples) if self.use_stash else 0
             s = dict(rays=torch.zeros(N, 8, device=d), projs=torch.zeros(N, device=d),
+                     stash=torch.empty(nb, dtype=torch.uint8, device=d) if nb else None,
                      mask=torch.ones(N, device=d, dtype=torch.uint8) if with_mask else None,
                      t_rand=torch.zeros(N, self.n_samples, device=d) if self.perturb else None,
                      loss=torch.zeros(2, device=d), dacc=torch.zeros(N, device=d), acc=torch.zeros(N, device=d))
@@ -214,7 +217,7 @@ class NAFEngine:
 
     def _run_fwd_bwd(self, s, key):
         if not self.use_cuda_graph:
-            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"])
+            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], stash=s["stash"])
             return
         g = self._graphs.get(key)
         if g is None:
@@ -222,12 +225,12 @@ class NAFEngine:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"])
+                self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], stash=s["stash"])
                 self.flat_grad.zero_()  # the gradient is zero between steps (Adam clears it)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"])
+                self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], stash=s["stash"])
             self._graphs[key] = g
             # capture does not execute: replay below performs the first real step
         g.replay()

@@ -1,8 +1,11 @@
 """Autograd front-ends of the fused kernels (encode + MLP [+ sampling + ray integral]).
 
-Nothing but the sample positions (or the rays) is saved for backward: the backward kernel
-recomputes the gather and the activations tile by tile (the table is L2 resident), so no
-[P, 32] activation ever goes to HBM.
+What is saved for backward: the sample positions (or the rays) and -- in the tensor-core mode --
+the "stash" the forward kernel leaves behind: the bf16 (hi|lo) images of the encodings, 128 B per
+point, already in the operand layout of the backward kernel's MMAs.  The backward kernel reloads
+them with full-line loads (no second table gather: the gather is bound by the SM's one
+address-divergent wavefront per clock, not by bytes) and recomputes the MLP activations tile by
+tile.  Without a stash (fp32 SIMT mode, inference) everything is recomputed from the points.
 """
 from __future__ import annotations
 
@@ -64,8 +67,15 @@ def _workspace(mlp_struct, device):
     return ws
 
 
+def stash_bytes(meta: NetMeta, table, params, n_points: int) -> int:
+    """Size of the encoding stash for n_points in the current arithmetic mode (0: not used)."""
+    grid = meta.grid(table)
+    mlp = meta.mlp(params)
+    return int(_lib.lib().nafb_density_stash_bytes(ctypes.byref(grid), ctypes.byref(mlp), int(n_points)))
+
+
 def density_forward(meta: NetMeta, table, params, *, pts=None, rays=None, t_rand=None, n_samples=0, perturb=False,
-                    voxels=None, want_acc=False, want_pts=False, want_z=False, want_sigma=True, flags=None):
+                    voxels=None, want_acc=False, want_pts=False, want_z=False, want_sigma=True, flags=None, want_stash=False):
     """Low-level launcher shared by the autograd functions and the engine. Returns dict of outputs."""
     L_ = _lib.lib()
     dev = table.device
@@ -91,16 +101,21 @@ def density_forward(meta: NetMeta, table, params, *, pts=None, rays=None, t_rand
     acc = torch.zeros(rays.shape[0], device=dev, dtype=torch.float32) if want_acc else None
     z = torch.empty(rays.shape[0], n_samples, device=dev, dtype=torch.float32) if want_z else None
     po = torch.empty(rays.shape[0], n_samples, 3, device=dev, dtype=torch.float32) if want_pts else None
+    stash = None
+    if want_stash:
+        nb = int(L_.nafb_density_stash_bytes(ctypes.byref(grid), ctypes.byref(mlp), P))
+        stash = torch.empty(nb, dtype=torch.uint8, device=dev) if nb else None
     with torch.cuda.device(dev):
         _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), src, _lib.ptr(sigma), _lib.ptr(acc),
-                                           _lib.ptr(z), _lib.ptr(po), _lib.ptr(flags), _lib.stream_ptr()))
-    out.update(sigma=sigma, acc=acc, z_vals=z, pts=po)
+                                           _lib.ptr(z), _lib.ptr(po), _lib.ptr(flags), _lib.ptr(stash), _lib.stream_ptr()))
+    out.update(sigma=sigma, acc=acc, z_vals=z, pts=po, stash=stash)
     return out
 
 
 def density_backward(meta: NetMeta, table, params, dsig_or_dacc, grad_table, grad_params, *, pts=None, rays=None, t_rand=None,
-                     n_samples=0, perturb=False):
-    """Accumulates into grad_table / grad_params (list aligned with params; entries may be None)."""
+                     n_samples=0, perturb=False, stash=None):
+    """Accumulates into grad_table / grad_params (list aligned with params; entries may be None).
+    `stash` is what density_forward(want_stash=True) returned for the same points, or None."""
     L_ = _lib.lib()
     dev = table.device
     grid = meta.grid(table)
@@ -114,9 +129,13 @@ def density_backward(meta: NetMeta, table, params, dsig_or_dacc, grad_table, gra
                            n_rays=rays.shape[0], n_samples=n_samples, perturb=int(bool(perturb)))
         src = _lib.SRC_RAYS
     ws = _workspace(mlp, dev)
+    if stash is not None:
+        P = pts.shape[0] if pts is not None else rays.shape[0] * n_samples
+        if stash.numel() != int(L_.nafb_density_stash_bytes(ctypes.byref(grid), ctypes.byref(mlp), P)):
+            stash = None  # the arithmetic mode changed between forward and backward: recompute
     with torch.cuda.device(dev):
         _lib.check(L_.nafb_density_backward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), src, _lib.ptr(dsig_or_dacc),
-                                            _lib.ptr(grad_table), ctypes.byref(grads), _lib.ptr(ws), _lib.stream_ptr()))
+                                            _lib.ptr(grad_table), ctypes.byref(grads), _lib.ptr(ws), _lib.ptr(stash), _lib.stream_ptr()))
 
 
 class DensityFn(Function):
@@ -127,9 +146,10 @@ class DensityFn(Function):
         pts = _prep(pts.detach(), "inputs")
         table_c = _prep(table.detach(), "embeddings")
         ps = [_prep(p.detach(), "weight") for p in params]
-        out = density_forward(meta, table_c, ps, pts=pts, flags=flags)
+        need_grad = any(ctx.needs_input_grad[i] for i in (1, *range(4, 4 + len(params))))
+        out = density_forward(meta, table_c, ps, pts=pts, flags=flags, want_stash=need_grad)
         ctx.save_for_backward(pts, table_c, *ps)
-        ctx.meta = meta
+        ctx.meta, ctx.stash = meta, out["stash"]
         return out["sigma"].view(-1, 1)
 
     @staticmethod
@@ -140,7 +160,8 @@ class DensityFn(Function):
         need_table = ctx.needs_input_grad[1]
         grad_table = torch.zeros_like(table) if need_table else None
         grad_params = [torch.zeros_like(p) for p in ps]
-        density_backward(meta, table, ps, dsigma, grad_table, grad_params, pts=pts)
+        density_backward(meta, table, ps, dsigma, grad_table, grad_params, pts=pts, stash=ctx.stash)
+        ctx.stash = None
         return (None, grad_table, None, None, *grad_params)
 
 
@@ -153,10 +174,11 @@ class RenderFn(Function):
         table_c = _prep(table.detach(), "embeddings")
         ps = [_prep(p.detach(), "weight") for p in params]
         tr = _prep(t_rand.detach(), "t_rand") if (perturb and t_rand is not None) else None
+        need_grad = any(ctx.needs_input_grad[i] for i in (2, *range(6, 6 + len(params))))
         out = density_forward(meta, table_c, ps, rays=rays, t_rand=tr, n_samples=n_samples, perturb=perturb, want_acc=True,
-                              want_pts=True, want_z=True, want_sigma=False)
+                              want_pts=True, want_z=True, want_sigma=False, want_stash=need_grad)
         ctx.save_for_backward(rays, table_c, *( [tr] if tr is not None else [] ), *ps)
-        ctx.has_tr = tr is not None
+        ctx.has_tr, ctx.stash = tr is not None, out["stash"]
         ctx.meta, ctx.n_samples, ctx.perturb = meta, n_samples, perturb
         ctx.mark_non_differentiable(out["pts"], out["z_vals"])
         return out["acc"], out["pts"], out["z_vals"]
@@ -171,5 +193,6 @@ class RenderFn(Function):
         grad_table = torch.zeros_like(table) if ctx.needs_input_grad[2] else None
         grad_params = [torch.zeros_like(p) for p in ps]
         density_backward(ctx.meta, table, ps, dacc, grad_table, grad_params, rays=rays, t_rand=tr, n_samples=ctx.n_samples,
-                         perturb=ctx.perturb)
+                         perturb=ctx.perturb, stash=ctx.stash)
+        ctx.stash = None
         return (None, None, grad_table, None, None, None, *grad_params)

@@ -271,6 +271,44 @@ def test_density_fused_vs_unfused_and_oracle(mlp_mode):
         np.testing.assert_allclose(a.cpu().numpy(), b.grad.numpy(), rtol=2e-3, atol=2e-5)
 
 
+def test_density_backward_stash_and_aggregated_scatter():
+    """tcgen05 mode: (a) backward from the encoding stash == backward that gathers again; (b) points that are
+    consecutive samples of rays (long runs of lanes in one coarse cell -> warp-aggregated scatter) give the
+    same table gradient as the unfused hash-grid backward (one atomic per corner) and as the CPU oracle."""
+    from neuralvolumetricreconstructionformedicalimages_b200.fused import density_backward, density_forward
+    torch.manual_seed(3)
+    rng = np.random.default_rng(3)
+    net = _chest_net(table_scale=0.3)
+    meta = net.fused_meta()
+    table = net.encoder.embeddings.detach()
+    ps = [p.detach() for p in net.flat_params()]
+    N, S = 37, 96                                  # 3552 points: ragged last tile, warps straddle rays
+    rays = torch.from_numpy(make_rays(N, rng)).to(DEV)
+    t_rand = torch.rand(N, S, device=DEV)
+    dacc = torch.randn(N, device=DEV)
+    grads = []
+    for use_stash in (True, False):
+        out = density_forward(meta, table, ps, rays=rays, t_rand=t_rand, n_samples=S, perturb=True, want_acc=True, want_sigma=False,
+                              want_pts=True, want_stash=use_stash)
+        assert (out["stash"] is not None) == use_stash
+        gt = torch.zeros_like(table)
+        gp = [torch.zeros_like(p) for p in ps]
+        density_backward(meta, table, ps, dacc, gt, gp, rays=rays, t_rand=t_rand, n_samples=S, perturb=True, stash=out["stash"])
+        grads.append([gt] + gp)
+        pts = out["pts"]
+    for a, b in zip(*grads):
+        sc = float(b.abs().max())
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-6 * sc)
+    # (b) against the oracle on the same points with d sigma = dacc * delta
+    o = _oracle_net(net)
+    oret = naf.render(rays.cpu(), o, S, True, t_rand=t_rand.cpu())
+    assert np.array_equal(bits(pts.cpu().numpy()), bits(oret["pts"].numpy()))
+    (oret["acc"] * dacc.cpu()).sum().backward()
+    for a, b in zip(grads[0], o.parameters()):
+        gb = b.grad.numpy()
+        np.testing.assert_allclose(a.cpu().numpy(), gb, rtol=5e-3, atol=2e-5 * np.abs(gb).max())
+
+
 @both_modes
 def test_density_ragged_and_range(mlp_mode):
     net = _chest_net()
