@@ -66,7 +66,7 @@ int nafb_make_grid_params(const nafb_grid *g, GridParams *out) {
         lp.s1 = strides[1];
         lp.s2 = strides[2];
     }
-    for (uint32_t l = g->L; l < NAFB_MAX_LEVELS; ++l) out->lv[l] = LevelParams{0, 1, 0, 0.f, 0, 0, 0};
+    for (uint32_t l = g->L; l < NAFB_MAX_LEVELS; ++l) out->lv[l] = LevelParams{0, 1, 0, 0.f, 0, 0, 0, 0};
     return NAFB_OK;
 }
 

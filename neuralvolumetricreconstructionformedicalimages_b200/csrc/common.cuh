@@ -24,13 +24,14 @@ int nafb_sm_count();
 // Per-level constants of the multi-resolution grid, evaluated once on the host and passed
 // BY VALUE in the kernel parameter block (constant bank: no loads, no runtime `%` for the
 // power-of-two levels).  Restates hashencoder.cu:55-74 and :98-100.
-struct LevelParams {
+struct alignas(16) LevelParams {   // 32 bytes: two 128-bit loads when a kernel keeps the table in shared memory
     uint32_t offset;   // entry offset of the level                         (hashencoder.cu:94)
     uint32_t size;     // hashmap_size = offsets[l+1]-offsets[l]            (:98)
     uint32_t mask;     // size-1 if size is a power of two, else 0 (use `% size`)
     float scale;       // fma(exp2f(l), H, -1)                              (:99)
     uint32_t s1, s2;   // uint32-wrapped linear strides (res+1), (res+1)^2  (:61-65)
     uint32_t hashed;   // 1: xor-prime hash, 0: (wrapped) linear index      (:67-71)
+    uint32_t pad;
 };
 
 struct GridParams {
@@ -46,7 +47,9 @@ int nafb_make_grid_params(const nafb_grid *g, GridParams *out);
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint32_t wrap_index(uint32_t idx, const LevelParams &lp) {
-    return lp.mask ? (idx & lp.mask) : (idx % lp.size);
+    // (idx % size): power-of-two sizes are a mask; for the dense levels the linear index of an in-range
+    // position is already < size, so the division is only reached by out-of-range inputs
+    return lp.mask ? (idx & lp.mask) : (idx < lp.size ? idx : idx % lp.size);
 }
 
 // get_grid_index<3,C>(ch=0)/C  (hashencoder.cu:55-74); `linear` already carries the uint32 wrap.

@@ -95,9 +95,10 @@ __device__ __forceinline__ void gather_half(const GridParams &gp, const float (&
     }
 }
 
-// Gradient scatter of one point.  `genc` holds all 32 columns of d(encoding) of the point; the thread
-// scatters levels l = 2*li + half (even levels on half 0, odd on half 1: the contended coarse levels
-// and the all-miss fine levels are split evenly over the two halves of the CTA).
+// Gradient scatter of ONE level of one point: d(encoding) of the level is read from the point's TMEM lane
+// (`taddr`: C columns), the 8 corner reductions go to the gradient table.  One copy of this code serves all
+// levels and all call sites (__noinline__): the backward kernel calls it from the wait slots of the NEXT tile's
+// MMA chain, so the reductions drain through the LSU while the tensor core and the epilogues work.
 //
 // Coarse levels are WARP-AGGREGATED: the 32 lanes of a warp hold 32 consecutive sample points (for the
 // ray source: consecutive samples of one ray), which fall into a few grid cells only.  Lanes of one
@@ -106,75 +107,112 @@ __device__ __forceinline__ void gather_half(const GridParams &gp, const float (&
 // reductions of the run.  The L2 atomic unit serialises per address (and the few hot lines of a coarse
 // level live in a handful of L2 slices), so the number of reductions -- not their bytes -- is what the
 // backward pass pays for.  The choice is made per warp and level from the number of runs (ballot).
-constexpr int AGG_LI = 4;          // levels 0 .. 2*AGG_LI-1 may be aggregated
+constexpr int AGG_LEVELS = 8;      // levels 0 .. AGG_LEVELS-1 may be aggregated
 constexpr int AGG_MAX_RUNS = 20;   // aggregate when the warp has at most this many runs
 
 template <int C>
-__device__ __forceinline__ void scatter_levels(const GridParams &gp, const float (&x01)[3], const int half, const bool valid, const unsigned lane,
-                                               const float (&genc)[32], float *grad_table, const int dbg) {
-    constexpr int NL = 32 / C;  // levels of the grid
-#pragma unroll
-    for (int li = 0; li < NL / 2; ++li) {
-        const int l = 2 * li + half;
-        if ((dbg & 4) && l < 6) continue;
-        if ((dbg & 8) && l >= 6) continue;
-        const LevelParams lp = gp.lv[l];
-        float *tab = grad_table + (size_t)lp.offset * C;
-        float ge[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) ge[c] = half ? genc[(2 * li + 1) * C + c] : genc[(2 * li) * C + c];
-        uint32_t g[3];
-        float f[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
-        bool direct = true;
-        if (li < AGG_LI && !(dbg & 16)) {
-            // runs of equal cells among consecutive lanes (invalid lanes: a run of their own, never issued)
-            const uint32_t k0 = valid ? (g[0] | (g[1] << 16)) : 0xffffffffu, k1 = valid ? g[2] : 0xffffffffu;
-            const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
-            const bool head = lane == 0 || p0 != k0 || p1 != k1;
-            const uint32_t heads = __ballot_sync(0xffffffffu, head);
-            if (__popc(heads) <= AGG_MAX_RUNS) {
-                direct = false;
-                float v[8][C];
-#pragma unroll
-                for (uint32_t idx = 0; idx < 8; ++idx) {
-                    float w = 1.0f;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
-#pragma unroll
-                    for (int c = 0; c < C; ++c) v[idx][c] = valid ? __fmul_rn(w, ge[c]) : 0.f;
-                }
-                const uint32_t above = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));  // bit j: lane+1+j starts a new run
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const bool same = (lane + o < 32) && ((above & ((1u << o) - 1u)) == 0u);
-#pragma unroll
-                    for (uint32_t idx = 0; idx < 8; ++idx)
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float up = __shfl_down_sync(0xffffffffu, v[idx][c], o);
-                            if (same) v[idx][c] += up;
-                        }
-                }
-                if (head && valid) {
-#pragma unroll
-                    for (uint32_t idx = 0; idx < 8; ++idx)
-                        red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v[idx]);
-                }
-            }
-        }
-        if (direct && valid) {
+__device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, const int l, const float x0, const float x1, const float x2,
+                                         const uint32_t taddr, const bool valid, const bool try_agg, float *__restrict__ grad_table) {
+    const unsigned lane = threadIdx.x & 31u;
+    float ge[C];
+    umma::tmem_ldn<C>(taddr, ge);
+    const LevelParams lp = lvs[l];
+    float *tab = grad_table + (size_t)lp.offset * C;
+    uint32_t g[3];
+    float f[3];
+    locate(x0, lp.scale, g[0], f[0]);
+    locate(x1, lp.scale, g[1], f[1]);
+    locate(x2, lp.scale, g[2], f[2]);
+    umma::tmem_wait_ld();
+    if (try_agg) {
+        // runs of equal cells among consecutive lanes (invalid lanes: a run of their own, never issued)
+        const uint32_t k0 = valid ? (g[0] | (g[1] << 16)) : 0xffffffffu, k1 = valid ? g[2] : 0xffffffffu;
+        const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
+        const bool head = lane == 0 || p0 != k0 || p1 != k1;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        if (__popc(heads) <= AGG_MAX_RUNS) {
+            float v[8][C];
 #pragma unroll
             for (uint32_t idx = 0; idx < 8; ++idx) {
                 float w = 1.0f;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
-                float v[C];
 #pragma unroll
-                for (int c = 0; c < C; ++c) v[c] = __fmul_rn(w, ge[c]);
-                red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v);
+                for (int c = 0; c < C; ++c) v[idx][c] = valid ? __fmul_rn(w, ge[c]) : 0.f;
             }
+            const uint32_t above = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));  // bit j: lane+1+j starts a new run
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const bool same = (lane + o < 32) && ((above & ((1u << o) - 1u)) == 0u);
+#pragma unroll
+                for (uint32_t idx = 0; idx < 8; ++idx)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float up = __shfl_down_sync(0xffffffffu, v[idx][c], o);
+                        if (same) v[idx][c] += up;
+                    }
+            }
+            if (head && valid) {
+#pragma unroll
+                for (uint32_t idx = 0; idx < 8; ++idx)
+                    red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v[idx]);
+            }
+            return;
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            float w = 1.0f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __fmul_rn(w, ge[c]);
+            red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v);
+        }
+    }
+}
+
+// Backward pass without a stash: gather the thread's 16 encoding columns level by level (rolled loop, one copy of
+// the code) and drop them as bf16 (hi, lo) into the operand tile.
+template <int C>
+__device__ __noinline__ void gather_half_to_smem(const LevelParams *__restrict__ lvs, const float *__restrict__ table, const float x0,
+                                                 const float x1, const float x2, const int half, uint8_t *hi, uint8_t *lo, const uint32_t row,
+                                                 const uint32_t chunk0, const uint32_t sbo) {
+    constexpr int LH = 16 / C;
+#pragma unroll 1
+    for (int li = 0; li < LH; ++li) {
+        const LevelParams lp = lvs[half * LH + li];
+        const float *__restrict__ tab = table + (size_t)lp.offset * C;
+        uint32_t g[3];
+        float f[3];
+        locate(x0, lp.scale, g[0], f[0]);
+        locate(x1, lp.scale, g[1], f[1]);
+        locate(x2, lp.scale, g[2], f[2]);
+        float v[8][C];
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx)
+            load_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v[idx]);
+        float res[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) res[c] = 0.f;
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            float w = 1.0f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
+#pragma unroll
+            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[idx][c], res[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const uint32_t col = (uint32_t)(li * C + c);
+            const uint32_t off = umma::canon_off(row, chunk0 + 2 * half + (col >> 3), LBO, sbo) + (col & 7u) * 2u;
+            __nv_bfloat16 h, lw;
+            umma::split_bf16(res[c], h, lw);
+            *reinterpret_cast<__nv_bfloat16 *>(hi + off) = h;
+            *reinterpret_cast<__nv_bfloat16 *>(lo + off) = lw;
         }
     }
 }
@@ -458,9 +496,10 @@ __global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, c
 // plus 1536 B of slack so that the 128-feature window starting at the G block stays inside the allocation.
 constexpr uint32_t BX_SBO = 2560, BX_HALF = 16 * 2560 + 1536;
 constexpr uint32_t CH_H0 = 0, CH_ENC = 4, CH_H1 = 8, CH_G = 16;
-constexpr uint32_t BWD_SMEM = 2 * BX_HALF + 2 * W_HALF + sizeof(SmallParams) + sizeof(TileCtl) + 2 * TILE * sizeof(float) + 8 * 80 * sizeof(float) + 128;
-// TMEM columns
-constexpr uint32_t T_S = 0, T_DENC = 32, T_DW0 = 64, T_DW1 = 96, T_DW2 = 128, T_COLS = 256;
+constexpr uint32_t BWD_SMEM = 2 * BX_HALF + 2 * W_HALF + sizeof(SmallParams) + sizeof(TileCtl) + 2 * TILE * sizeof(float) + 8 * 80 * sizeof(float) +
+                              NAFB_MAX_LEVELS * sizeof(LevelParams) + 128;
+// TMEM columns.  d(encoding) is double buffered: the buffer of tile i is scattered while tile i+1 runs.
+constexpr uint32_t T_S = 0, T_DENC0 = 32, T_DW0 = 64, T_DW1 = 96, T_DW2 = 128, T_DENC1 = 192, T_COLS = 256;
 
 // offsets inside one CTA's slot of the partials workspace (floats) -- matches density.cu's MlpLayout for this net
 constexpr int PW0 = 0, PW1 = 1024, PW2 = 2048, PW3 = 4096, PB0 = 4128, PB1 = 4160, PB2 = 4192, PB3 = 4224, PTOTAL = 4228;
@@ -477,10 +516,12 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
     float *xchg = reinterpret_cast<float *>(ctl + 1);  // [128] head partial dot products of half 1
     float *xchg2 = xchg + TILE;                         // [128] head pre-activation gradients
     float *wred = xchg2 + TILE;                         // [8 warps][80]: per-warp column sums flushed at the end
+    LevelParams *lvs = reinterpret_cast<LevelParams *>(wred + 8 * 80);   // 16-byte aligned (all blocks above are multiples of 16 B)
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int r = t & 127, half = t >> 7;
     load_weight_images(mp, W_hi, W_lo, small);
+    if (t < NAFB_MAX_LEVELS) lvs[t] = gp.lv[t];
     // the slack / unused blocks are read (as don't-care rows) by the windowed dW MMAs: keep them finite
     for (uint32_t i = t; i < 2 * BX_HALF / 16; i += NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (t == 0) {
@@ -518,8 +559,27 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
     };
     auto desc = [&](uint32_t base, uint32_t chunk, uint32_t lbo, uint32_t sbo) { return umma::make_desc(base + chunk * LBO, lbo, sbo); };
 
+    // ---- deferred scatter: the gradient of the PREVIOUS tile (still in TMEM) is scattered, one slot at a time, after
+    // each MMA issue of the current tile.  Thread (r, half) owns levels l = 2*li + half (even levels on half 0, odd on
+    // half 1: the contended coarse levels and the all-miss fine levels are split evenly over the two halves of the CTA).
+    constexpr int NLH = 16 / C;   // levels per thread
+    float xp[3] = {0.f, 0.f, 0.f};
+    bool valid_prev = false, have_prev = false;
+    uint32_t tdenc_prev = 0;      // TMEM address (lane base included) of the previous tile's d(encoding)
+    const bool do_scatter = grad_table != nullptr && !(dbg & 1);
+    const bool agg_on = !(dbg & 16);
+    auto scatter_slot = [&](const int slot) {   // 8 slots cover the NLH levels of the thread
+        if (!have_prev) return;
+        for (int li = slot * NLH / 8; li < (slot + 1) * NLH / 8; ++li) {
+            const int l = 2 * li + half;
+            scatter_one<C>(lvs, l, xp[0], xp[1], xp[2], tdenc_prev + (uint32_t)(l * C), valid_prev, agg_on && l < AGG_LEVELS, grad_table);
+        }
+    };
+
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t T_DENC = (it & 1u) ? T_DENC1 : T_DENC0;
         const uint64_t p = tile * TILE + r;
         const bool valid = p < P;
         float x[3] = {0.f, 0.f, 0.f};
@@ -541,14 +601,14 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         if (stash) {
             load_stash_half_row(A_hi, A_lo, r, CH_ENC, half, BX_SBO, stash + tile * ST_TILE);
         } else {
-            float enc[16];
             if (dbg & 2) {
+                float enc[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) enc[i] = x01[i % 3];
+                store_half_row(A_hi, A_lo, r, CH_ENC, half, BX_SBO, enc);
             } else {
-                gather_half<C>(gp, x01, half, enc);
+                gather_half_to_smem<C>(lvs, gp.table, x01[0], x01[1], x01[2], half, A_hi, A_lo, r, CH_ENC, BX_SBO);
             }
-            store_half_row(A_hi, A_lo, r, CH_ENC, half, BX_SBO, enc);
         }
         float v[16];
         // ---------------- forward layer 0
@@ -559,6 +619,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
                              umma::make_desc(w_hi + W0_OFF, LBO, W0_SBO), umma::make_desc(w_lo + W0_OFF, LBO, W0_SBO), 256, 256, 2, ID_FWD, false);
             umma::commit(&ctl->mbar);
         }
+        if (do_scatter) { scatter_slot(0); scatter_slot(1); }
         wait_mma();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
@@ -573,6 +634,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
                              umma::make_desc(w_hi + W1_OFF, LBO, W1_SBO), umma::make_desc(w_lo + W1_OFF, LBO, W1_SBO), 256, 256, 2, ID_FWD, false);
             umma::commit(&ctl->mbar);
         }
+        if (do_scatter) { scatter_slot(2); }
         wait_mma();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
@@ -587,6 +649,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
                              umma::make_desc(w_hi + W2_OFF, LBO, W2_SBO), umma::make_desc(w_lo + W2_OFF, LBO, W2_SBO), 256, 256, 4, ID_FWD, false);
             umma::commit(&ctl->mbar);
         }
+        if (do_scatter) { scatter_slot(3); }
         wait_mma();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
@@ -632,6 +695,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
                              2 * W2_SBO, 2, ID_DX, false);
             umma::commit(&ctl->mbar);
         }
+        if (do_scatter) { scatter_slot(4); }
         wait_mma();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
@@ -653,6 +717,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
                              umma::make_desc(w_hi + W1_OFF, W1_SBO, LBO), umma::make_desc(w_lo + W1_OFF, W1_SBO, LBO), 256, 2 * W1_SBO, 2, ID_DX, false);
             umma::commit(&ctl->mbar);
         }
+        if (do_scatter) { scatter_slot(5); }
         wait_mma();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
@@ -674,17 +739,20 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
                              umma::make_desc(w_hi + W0_OFF, W0_SBO, LBO), umma::make_desc(w_lo + W0_OFF, W0_SBO, LBO), 256, 2 * W0_SBO, 2, ID_DX, true);
             umma::commit(&ctl->mbar);
         }
+        if (do_scatter) { scatter_slot(6); scatter_slot(7); }
         wait_mma();
-        {
-            float ge[32];
-            umma::tmem_ld32(tmem + lane_base + T_DENC, ge);
-            umma::tmem_wait_ld();
-            umma::fence_before_sync();
-            // ---------------- scatter d(encoding) into the gradient table
-            if (grad_table && !(dbg & 1)) scatter_levels<C>(gp, x01, half, valid, lane, ge, grad_table, dbg);
-        }
+        // d(encoding) of this tile stays in TMEM; it is scattered from the wait slots of the next tile (or below)
+        xp[0] = x01[0]; xp[1] = x01[1]; xp[2] = x01[2];
+        valid_prev = valid;
+        have_prev = true;
+        tdenc_prev = tmem + lane_base + T_DENC;
         first_tile = false;
+        umma::fence_before_sync();
         __syncthreads();
+    }
+    if (do_scatter) {   // the last tile of this CTA
+#pragma unroll 1
+        for (int slot = 0; slot < 8; ++slot) scatter_slot(slot);
     }
 
     // ================= flush the MLP gradients of this CTA into its slot of the partials workspace

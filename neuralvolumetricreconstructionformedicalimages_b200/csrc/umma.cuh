@@ -122,6 +122,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// N consecutive 32-bit columns (N = 1, 2, 4, 8) of this thread's TMEM lane
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[N]) {
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8, "tmem_ldn: N must be 1, 2, 4 or 8");
+    uint32_t r[8];
+    if constexpr (N == 1)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r[0]) : "r"(taddr));
+    else if constexpr (N == 2)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+    else if constexpr (N == 4)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    else
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- canonical layout + bf16x2 split stores
