@@ -166,9 +166,11 @@ int nafb_ray_integral_backward(const float *dacc, uint32_t out_dim, const float 
  * Masked, chunk-wise MSE of train.py:69-127 / loss.py:26-46:
  *   loss = sum_chunks mean_{r in chunk, mask[r]} (target[r]-pred[r])^2 ;  dpred[r] = dloss/dpred[r] * gscale.
  * mask may be NULL (all rays valid); chunk == 0 means one chunk.  loss_out[0] = loss,
- * loss_out[1] = number of valid rays.  Single deterministic block. */
-int nafb_mse_loss(const float *pred, const float *target, const uint8_t *mask, uint32_t n, uint32_t chunk,
-                  float gscale, float *loss_out, float *dpred, nafb_stream_t stream);
+ * loss_out[1] = number of valid rays.  Single deterministic block (one warp per chunk, chunk means
+ * added in chunk order).  zero_pred != 0: pred is cleared once consumed (the fused engine accumulates
+ * the next step's projections into the same buffer with atomics). */
+int nafb_mse_loss(float *pred, const float *target, const uint8_t *mask, uint32_t n, uint32_t chunk,
+                  float gscale, float *loss_out, float *dpred, int zero_pred, nafb_stream_t stream);
 
 /* ------------------------------------------------------------------ optimiser
  * torch.optim.Adam (trainer.py:54: betas (0.9,0.999), eps 1e-8, no weight decay, no amsgrad),

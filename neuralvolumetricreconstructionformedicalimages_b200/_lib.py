@@ -63,7 +63,7 @@ _SIGNATURES = {
     "nafb_sample_points": (ctypes.c_int, [ctypes.POINTER(Sampler), c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
     "nafb_ray_integral_forward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_ray_integral_backward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
-    "nafb_mse_loss": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, u32, u32, ctypes.c_float, c_f32p, c_f32p, ctypes.c_void_p]),
+    "nafb_mse_loss": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, u32, u32, ctypes.c_float, c_f32p, c_f32p, ctypes.c_int, ctypes.c_void_p]),
     "nafb_set_mlp_mode": (ctypes.c_int, [ctypes.c_int]),
     "nafb_microbench": (ctypes.c_int, [ctypes.c_int, c_f32p, u32, ctypes.c_int, c_f32p, ctypes.POINTER(u64), ctypes.c_void_p]),
     "nafb_selftest_umma": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_void_p]),

@@ -26,7 +26,8 @@ uint64_t nafb_tc_stash_bytes(uint64_t n_points);
 int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
                        float *pts, int32_t *flags, void *stash, cudaStream_t s);
 int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
-                       float *grad_table, float *partials, const void *stash, int grid, cudaStream_t s);
+                       float *grad_table, float *partials, const void *stash, long long *stamps, int grid, cudaStream_t s);
+int nafb_tc_bwd_grid(uint64_t n_tiles);
 static int g_mlp_mode = 0;  // 0: tensor cores when the configuration allows, 1: fp32 SIMT everywhere
 
 namespace {
@@ -467,14 +468,31 @@ __global__ void __launch_bounds__(TILE, 2) k_density_bwd(const GridParams gp, co
     for (int i = threadIdx.x; i < lo.total; i += blockDim.x) mine[i] = dWs[i];
 }
 
-// gW/gb += sum over CTAs of the partials (fixed order: deterministic)
+// gW/gb += sum over CTAs of the partials.  Block = 32 outputs x 8 slices of the CTA range; every slice sums its CTAs in
+// order, the 8 slice sums are combined in order: the summation tree is fixed (deterministic), loads are coalesced.
 __global__ void __launch_bounds__(256) k_reduce_partials(const nafb_mlp mp, const nafb_mlp_grads gr, const float *__restrict__ partials,
                                                          int n_blocks) {
+    __shared__ float part[8][33];
     const MlpLayout lo = make_layout(mp);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= lo.total) return;
+    const int j = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + j;
     float s = 0.f;
-    for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * lo.total + i];
+    if (i < lo.total) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int b = k;
+        for (; b + 24 < n_blocks; b += 32) {
+            s0 += partials[(size_t)b * lo.total + i];
+            s1 += partials[(size_t)(b + 8) * lo.total + i];
+            s2 += partials[(size_t)(b + 16) * lo.total + i];
+            s3 += partials[(size_t)(b + 24) * lo.total + i];
+        }
+        for (; b < n_blocks; b += 8) s0 += partials[(size_t)b * lo.total + i];
+        s = (s0 + s1) + (s2 + s3);
+    }
+    part[k][j] = s;
+    __syncthreads();
+    if (k != 0 || i >= lo.total) return;
+    s = ((part[0][j] + part[1][j]) + (part[2][j] + part[3][j])) + ((part[4][j] + part[5][j]) + (part[6][j] + part[7][j]));
     for (int l = 0; l < lo.n_layers; ++l) {
         const int nw = lo.in[l] * lo.out[l];
         if (i >= lo.woff[l] && i < lo.woff[l] + nw) { if (gr.gW[l]) gr.gW[l][i - lo.woff[l]] += s; return; }
@@ -512,6 +530,10 @@ int bwd_grid(const MlpLayout &lo, uint64_t n_tiles) {
 }
 // upper bound used for the workspace size (independent of the problem size)
 int bwd_grid_max(const MlpLayout &lo) { return bwd_grid(lo, ~0ull); }
+uint64_t partials_bytes(const MlpLayout &lo) {
+    const int g_simt = bwd_grid_max(lo), g_tc = nafb_tc_bwd_grid(~0ull);
+    return (uint64_t)(g_simt > g_tc ? g_simt : g_tc) * lo.total * sizeof(float);
+}
 
 template <int SRC, int C>
 int launch_fwd(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, float *sigma, float *acc, float *z,
@@ -550,7 +572,7 @@ int launch_bwd(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp
     const int grid = bwd_grid(lo, n_tiles);
     k_density_bwd<SRC, C><<<grid, TILE, smem, s>>>(gp, mp, sp, P, dsig, grad_table, partials);
     NAFB_CHECK_LAUNCH("density_backward");
-    k_reduce_partials<<<(lo.total + 255) / 256, 256, 0, s>>>(mp, gr, partials, grid);
+    k_reduce_partials<<<(lo.total + 31) / 32, 256, 0, s>>>(mp, gr, partials, grid);
     NAFB_CHECK_LAUNCH("density_backward(reduce)");
     return NAFB_OK;
 }
@@ -601,7 +623,7 @@ int nafb_set_mlp_mode(int mode) {
 uint64_t nafb_density_backward_workspace_bytes(const nafb_mlp *mlp) {
     if (!mlp) return 0;
     const MlpLayout lo = make_layout(*mlp);
-    return (uint64_t)bwd_grid_max(lo) * lo.total * sizeof(float);
+    return partials_bytes(lo) + 4096;   // + debug area (phase time stamps of the tensor-core kernel)
 }
 
 int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src, const float *dsigma_or_dacc,
@@ -619,9 +641,10 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
     cudaStream_t s = (cudaStream_t)stream;
     if (g_mlp_mode == 0 && nafb_tc_config_ok(grid, mlp)) {
         const int grid_tc = nafb_tc_bwd_grid((P + TILE - 1) / TILE);
-        if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, grid_tc, s))) return rc;
         const MlpLayout lo = make_layout(*mlp);
-        k_reduce_partials<<<(lo.total + 255) / 256, 256, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
+        long long *stamps = reinterpret_cast<long long *>((char *)workspace + partials_bytes(lo));
+        if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps, grid_tc, s))) return rc;
+        k_reduce_partials<<<(lo.total + 31) / 32, 256, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
         NAFB_CHECK_LAUNCH("density_backward(reduce)");
         return NAFB_OK;
     }

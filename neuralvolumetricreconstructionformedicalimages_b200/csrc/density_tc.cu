@@ -507,7 +507,8 @@ constexpr int PW0 = 0, PW1 = 1024, PW2 = 2048, PW3 = 4096, PB0 = 4128, PB1 = 416
 template <int SRC, int C>
 __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           const float *__restrict__ dsig_or_dacc, float *__restrict__ grad_table,
-                                                          float *__restrict__ partials, const uint8_t *__restrict__ stash, const int dbg) {
+                                                          float *__restrict__ partials, const uint8_t *__restrict__ stash, long long *__restrict__ dbg_stamps,
+                                                          const int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *A_hi = smem, *A_lo = A_hi + BX_HALF;
     uint8_t *W_hi = A_lo + BX_HALF, *W_lo = W_hi + W_HALF;
@@ -576,10 +577,17 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         }
     };
 
+    // debug (dbg & 32): thread 0 of the first 4 CTAs stamps clock64() at every phase boundary into the 4 KB debug area at the
+    // end of the workspace: [cta][128 stamps]
+    long long *stamps = (dbg & 32) && t == 0 && blockIdx.x < 4 ? dbg_stamps + blockIdx.x * 128 : nullptr;
+    int n_st = 0;
+    auto stamp = [&]() { if (stamps && n_st < 128) stamps[n_st++] = clock64(); };
+
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t T_DENC = (it & 1u) ? T_DENC1 : T_DENC0;
+        stamp();   // 0: tile start
         const uint64_t p = tile * TILE + r;
         const bool valid = p < P;
         float x[3] = {0.f, 0.f, 0.f};
@@ -611,8 +619,10 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             }
         }
         float v[16];
+        stamp();   // 1: encodings in shared memory
         // ---------------- forward layer 0
         sync_issue();
+        stamp();   // 2: after the barrier
         if (t == 0) {
             umma::fence_after_sync();
             umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_ENC, LBO, BX_SBO), desc(a_lo, CH_ENC, LBO, BX_SBO),
@@ -620,7 +630,9 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             umma::commit(&ctl->mbar);
         }
         if (do_scatter) { scatter_slot(0); scatter_slot(1); }
+        stamp();
         wait_mma();
+        stamp();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
 #pragma unroll
@@ -635,7 +647,9 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             umma::commit(&ctl->mbar);
         }
         if (do_scatter) { scatter_slot(2); }
+        stamp();
         wait_mma();
+        stamp();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
 #pragma unroll
@@ -650,7 +664,9 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             umma::commit(&ctl->mbar);
         }
         if (do_scatter) { scatter_slot(3); }
+        stamp();
         wait_mma();
+        stamp();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
         // ---------------- head forward + backward (fp32 SIMT)
@@ -681,6 +697,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             acc_db2 += warp_colsum16(v, lane);
             if (half == 0) acc_db3 += warp_sum(gpre);
         }
+        stamp();   // head done
         store_half_row(A_hi, A_lo, r, CH_G, half, BX_SBO, v);
         // ---------------- backward layer 2: dW2 += G^T.[enc|h1];  d_enc = G.W2[:, :32];  dh1 = G.W2[:, 32:]
         sync_issue();
@@ -696,7 +713,9 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             umma::commit(&ctl->mbar);
         }
         if (do_scatter) { scatter_slot(4); }
+        stamp();
         wait_mma();
+        stamp();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
         {
@@ -718,7 +737,9 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             umma::commit(&ctl->mbar);
         }
         if (do_scatter) { scatter_slot(5); }
+        stamp();
         wait_mma();
+        stamp();
         umma::tmem_ld16(taddr + T_S, v);
         umma::tmem_wait_ld();
         {
@@ -740,7 +761,9 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             umma::commit(&ctl->mbar);
         }
         if (do_scatter) { scatter_slot(6); scatter_slot(7); }
+        stamp();
         wait_mma();
+        stamp();
         // d(encoding) of this tile stays in TMEM; it is scattered from the wait slots of the next tile (or below)
         xp[0] = x01[0]; xp[1] = x01[1]; xp[2] = x01[2];
         valid_prev = valid;
@@ -853,21 +876,21 @@ int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerPa
 
 template <int SRC, int C>
 static int launch_bwd_tc_t(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, const float *dsig, float *grad_table,
-                           float *partials, const uint8_t *stash, int grid, cudaStream_t s) {
+                           float *partials, const uint8_t *stash, long long *stamps, int grid, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_density_bwd_tc<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
         if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): %s", cudaGetErrorString(e));
         configured = true;
     }
-    k_density_bwd_tc<SRC, C><<<grid, NT, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, stash, nafb_debug_flags());
+    k_density_bwd_tc<SRC, C><<<grid, NT, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, nafb_debug_flags());
     NAFB_CHECK_LAUNCH("density_backward(tc)");
     return NAFB_OK;
 }
 
 int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
-                       float *grad_table, float *partials, const void *stash, int grid, cudaStream_t s) {
-#define CALL(S_, C_) launch_bwd_tc_t<S_, C_>(gp, mp, sp, P, dsig, grad_table, partials, (const uint8_t *)stash, grid, s)
+                       float *grad_table, float *partials, const void *stash, long long *stamps, int grid, cudaStream_t s) {
+#define CALL(S_, C_) launch_bwd_tc_t<S_, C_>(gp, mp, sp, P, dsig, grad_table, partials, (const uint8_t *)stash, stamps, grid, s)
     switch (gp.C) {
         case 1: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 1) : CALL(NAFB_SRC_RAYS, 1);
         case 2: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 2) : CALL(NAFB_SRC_RAYS, 2);

@@ -130,8 +130,7 @@ class NAFEngine:
         L_ = _lib.lib()
         tm = timer or _NoTimer()
         N = rays.shape[0]
-        with tm("zero_acc"):
-            acc.zero_()
+        # acc is zero on entry: allocated zeroed, and mse_loss clears it after reading (zero_pred)
         grid = self.meta.grid(self.table)
         mlp = self.meta.mlp(self.mlp_params)
         smp = self.meta.sampler(rays=rays.data_ptr(), t_rand=t_rand.data_ptr() if self.perturb else None, n_rays=N,
@@ -142,7 +141,7 @@ class NAFEngine:
                                                None, None, None, _lib.ptr(stash), st))
         chunk = int(self.loss_chunk or 0)
         with tm("mse_loss"):
-            _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), st))
+            _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), 1, st))
         with tm("density_bwd"):
             density_backward(self.meta, self.table, self.mlp_params, dacc, self.grad_table, self.grad_mlp, rays=rays, t_rand=t_rand,
                              n_samples=self.n_samples, perturb=self.perturb, stash=stash)

@@ -25,7 +25,7 @@ class _MaskedChunkMse(Function):
         dpred = torch.empty_like(pred)
         with torch.cuda.device(pred.device):
             _lib.check(L_.nafb_mse_loss(_lib.ptr(pred), _lib.ptr(target), _lib.ptr(mask), n, int(chunk or 0), 1.0, _lib.ptr(out),
-                                        _lib.ptr(dpred), _lib.stream_ptr()))
+                                        _lib.ptr(dpred), 0, _lib.stream_ptr()))
         ctx.save_for_backward(dpred)
         return out[0]
 
