@@ -20,13 +20,12 @@ The voxel query shards by slabs of the outermost index and needs no collective.
 from __future__ import annotations
 
 import ctypes
-import math
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, parallel
 from .fused import density_backward, density_forward, stash_bytes
 from .network.network import DensityNetwork
 
@@ -95,9 +94,10 @@ class NAFEngine:
         self.use_cuda_graph = use_cuda_graph
         self.use_stash = bool(use_stash)  # forward leaves the encodings (128 B/point) for backward instead of a second gather
         self.pg = process_group
-        self.world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        self.rank = dist.get_rank(process_group) if self.world_size > 1 else 0
+        self.rank, self.world_size = parallel.world_info(process_group)
         self._flatten()
+        if self.world_size > 1:   # replicas start identical
+            parallel.broadcast_(self.flat_param, 0, process_group)
         self._graphs = {}
         self._static = {}
 
@@ -175,7 +175,7 @@ class NAFEngine:
             self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], timer, stash=s["stash"])
             if self.world_size > 1:
                 with timer("all_reduce"):
-                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+                    parallel.allreduce_sum_(self.flat_grad, self.pg)
             self._adam(timer)
         return s["loss"][0]
 
@@ -209,8 +209,7 @@ class NAFEngine:
                 else:
                     s["t_rand"].copy_(t_rand, non_blocking=True)
             self._run_fwd_bwd(s, (N, mask is not None))
-            if self.world_size > 1:
-                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+            parallel.allreduce_sum_(self.flat_grad, self.pg)
             self._adam()
         return s["loss"][0]
 
@@ -266,8 +265,7 @@ class NAFEngine:
 
     def rank_slab(self, n1):
         """[i0, i1) of the outermost voxel index owned by this rank."""
-        per = math.ceil(n1 / self.world_size)
-        return min(self.rank * per, n1), min((self.rank + 1) * per, n1)
+        return parallel.shard_range(n1, self.rank, self.world_size)
 
     # ------------------------------------------------------------------ optimizer state (ckpt compatibility)
     def optimizer_state_dict(self):
