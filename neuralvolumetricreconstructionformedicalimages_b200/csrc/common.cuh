@@ -117,6 +117,47 @@ __device__ __forceinline__ void red_add_entry(float *base, uint32_t entry, const
     else { red_add_f32x4(p, v[0], v[1], v[2], v[3]); red_add_f32x4(p + 4, v[4], v[5], v[6], v[7]); }
 }
 
+// ---- x-neighbour pairs.  The two x-neighbours of a (y, z) corner are ADJACENT table entries about half of the time:
+// always on an xor-hashed level when x is even ((x ^ h) and ((x+1) ^ h) differ in bit 0 only), and e1 = e0 + 1 on a
+// linear level.  With C == 2 an adjacent pair is 16 contiguous bytes; when its lower entry sits on a 16-byte boundary one
+// 128-bit access serves both corners.  The gather is bound by address-divergent wavefronts and the scatter by the number
+// of reductions (not by bytes), so every merged pair is an operation saved.  `par` = bit 3 of the level's base address
+// ((uintptr_t)tab >> 3) & 1: entry e of the level is 16-byte aligned iff (e + par) is even.  Values and the order in
+// which the caller combines them are unchanged (bit-exact).
+__device__ __forceinline__ uint32_t addr_parity8(const void *p) { return (uint32_t)(reinterpret_cast<uintptr_t>(p) >> 3) & 1u; }
+
+template <int C>
+__device__ __forceinline__ void load_entry_pair(const float *__restrict__ tab, uint32_t par, uint32_t e0, uint32_t e1, float (&v0)[C],
+                                                float (&v1)[C]) {
+    if constexpr (C == 2) {
+        const uint32_t lo = e0 < e1 ? e0 : e1, hi = e0 < e1 ? e1 : e0;
+        if (hi - lo == 1u && ((lo + par) & 1u) == 0u) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(tab + 2 * (size_t)lo));
+            const bool fwd = e0 < e1;
+            v0[0] = fwd ? q.x : q.z; v0[1] = fwd ? q.y : q.w;
+            v1[0] = fwd ? q.z : q.x; v1[1] = fwd ? q.w : q.y;
+            return;
+        }
+    }
+    load_entry<C>(tab, e0, v0);
+    load_entry<C>(tab, e1, v1);
+}
+
+template <int C>
+__device__ __forceinline__ void red_add_entry_pair(float *tab, uint32_t par, uint32_t e0, uint32_t e1, const float (&v0)[C],
+                                                   const float (&v1)[C]) {
+    if constexpr (C == 2) {
+        const uint32_t lo = e0 < e1 ? e0 : e1, hi = e0 < e1 ? e1 : e0;
+        if (hi - lo == 1u && ((lo + par) & 1u) == 0u) {
+            const bool fwd = e0 < e1;
+            red_add_f32x4(tab + 2 * (size_t)lo, fwd ? v0[0] : v1[0], fwd ? v0[1] : v1[1], fwd ? v1[0] : v0[0], fwd ? v1[1] : v0[1]);
+            return;
+        }
+    }
+    red_add_entry<C>(tab, e0, v0);
+    red_add_entry<C>(tab, e1, v1);
+}
+
 __device__ __forceinline__ float leaky_relu(float x) { return x > 0.f ? x : 0.01f * x; }
 
 __device__ __forceinline__ float head_activation(float x, uint32_t head) {

@@ -26,6 +26,7 @@ namespace {
 
 constexpr int TILE = 128;
 constexpr int NT = 256;
+constexpr int NT_B = 288;  // backward: 8 epilogue warps + 1 MMA-issue warp
 constexpr uint32_t LBO = 128;  // bytes between adjacent 8-column chunks of a row group
 
 // ---- weights in shared memory (bf16 hi / lo, rows = output feature, chunks along the input)
@@ -75,10 +76,12 @@ __device__ __forceinline__ void gather_half(const GridParams &gp, const float (&
         float f[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
+        const uint32_t par = addr_parity8(tab);
         float v[8][C];
 #pragma unroll
-        for (uint32_t idx = 0; idx < 8; ++idx)
-            load_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v[idx]);
+        for (uint32_t j = 0; j < 4; ++j)   // (y, z) corner; the two x-neighbours share one access when adjacent + aligned
+            load_entry_pair<C>(tab, par, grid_entry3(lp, g[0], g[1] + (j & 1u), g[2] + (j >> 1)),
+                               grid_entry3(lp, g[0] + 1u, g[1] + (j & 1u), g[2] + (j >> 1)), v[2 * j], v[2 * j + 1]);
         float res[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) res[c] = 0.f;
@@ -118,6 +121,7 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
     umma::tmem_ldn<C>(taddr, ge);
     const LevelParams lp = lvs[l];
     float *tab = grad_table + (size_t)lp.offset * C;
+    const uint32_t par = addr_parity8(tab);
     uint32_t g[3];
     float f[3];
     locate(x0, lp.scale, g[0], f[0]);
@@ -154,22 +158,25 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
             }
             if (head && valid) {
 #pragma unroll
-                for (uint32_t idx = 0; idx < 8; ++idx)
-                    red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v[idx]);
+                for (uint32_t j = 0; j < 4; ++j)
+                    red_add_entry_pair<C>(tab, par, grid_entry3(lp, g[0], g[1] + (j & 1u), g[2] + (j >> 1)),
+                                          grid_entry3(lp, g[0] + 1u, g[1] + (j & 1u), g[2] + (j >> 1)), v[2 * j], v[2 * j + 1]);
             }
             return;
         }
     }
     if (valid) {
 #pragma unroll
-        for (uint32_t idx = 0; idx < 8; ++idx) {
-            float w = 1.0f;
+        for (uint32_t j = 0; j < 4; ++j) {
+            float v0[C], v1[C];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
-            float v[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) v[c] = __fmul_rn(w, ge[c]);
-            red_add_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v);
+            for (int c = 0; c < C; ++c) {
+                // same products as the corner loop of the reference: ((1 * a0) * a1) * a2 evaluated as (a0 * a1) * a2
+                v0[c] = __fmul_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.0f, f[0]), (j & 1u) ? f[1] : __fsub_rn(1.0f, f[1])), (j >> 1) ? f[2] : __fsub_rn(1.0f, f[2])), ge[c]);
+                v1[c] = __fmul_rn(__fmul_rn(__fmul_rn(f[0], (j & 1u) ? f[1] : __fsub_rn(1.0f, f[1])), (j >> 1) ? f[2] : __fsub_rn(1.0f, f[2])), ge[c]);
+            }
+            red_add_entry_pair<C>(tab, par, grid_entry3(lp, g[0], g[1] + (j & 1u), g[2] + (j >> 1)),
+                                  grid_entry3(lp, g[0] + 1u, g[1] + (j & 1u), g[2] + (j >> 1)), v0, v1);
         }
     }
 }
@@ -505,7 +512,7 @@ constexpr uint32_t T_S = 0, T_DENC0 = 32, T_DW0 = 64, T_DW1 = 96, T_DW2 = 128, T
 constexpr int PW0 = 0, PW1 = 1024, PW2 = 2048, PW3 = 4096, PB0 = 4128, PB1 = 4160, PB2 = 4192, PB3 = 4224, PTOTAL = 4228;
 
 template <int SRC, int C>
-__global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
+__global__ void __launch_bounds__(NT_B, 2) k_density_bwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           const float *__restrict__ dsig_or_dacc, float *__restrict__ grad_table,
                                                           float *__restrict__ partials, const uint8_t *__restrict__ stash, long long *__restrict__ dbg_stamps,
                                                           const int dbg) {
@@ -520,11 +527,11 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
     LevelParams *lvs = reinterpret_cast<LevelParams *>(wred + 8 * 80);   // 16-byte aligned (all blocks above are multiples of 16 B)
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int r = t & 127, half = t >> 7;
+    const int r = t & 127, half = (t >> 7) & 1;
     load_weight_images(mp, W_hi, W_lo, small);
     if (t < NAFB_MAX_LEVELS) lvs[t] = gp.lv[t];
     // the slack / unused blocks are read (as don't-care rows) by the windowed dW MMAs: keep them finite
-    for (uint32_t i = t; i < 2 * BX_HALF / 16; i += NT) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = t; i < 2 * BX_HALF / 16; i += NT_B) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (t == 0) {
         umma::mbar_init(&ctl->mbar, 1);
         umma::fence_mbar_init();
@@ -548,18 +555,76 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
     // of dW3 (16 columns) and db3
     float acc_db2 = 0.f, acc_db1 = 0.f, acc_db0 = 0.f, acc_dw3 = 0.f, acc_db3 = 0.f;
 
-    auto sync_issue = [&]() {
+
+    const uint64_t n_tiles = (P + TILE - 1) / TILE;
+    auto desc = [&](uint32_t base, uint32_t chunk, uint32_t lbo, uint32_t sbo) { return umma::make_desc(base + chunk * LBO, lbo, sbo); };
+
+    if (warp == 8) {
+        // ================= MMA warp: one lane issues every tcgen05.mma of the CTA.  The 8 epilogue warps ARRIVE on named
+        // barrier 1 when the operands of a phase are in shared memory (and their TMEM reads are done) and go on with other
+        // work (the deferred scatter); this warp SYNCs on it, issues the phase and commits to the mbarrier they wait on.
+        bool first = true;
+        uint32_t it = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t T_DENC = (it & 1u) ? T_DENC1 : T_DENC0;
+#pragma unroll 1
+            for (int ph = 0; ph < 6; ++ph) {
+                umma::named_bar_sync(1, NT_B);
+                if (lane == 0) {
+                    umma::fence_after_sync();
+                    switch (ph) {
+                        case 0:   // forward layer 0: enc . W0^T
+                            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_ENC, LBO, BX_SBO), desc(a_lo, CH_ENC, LBO, BX_SBO),
+                                             umma::make_desc(w_hi + W0_OFF, LBO, W0_SBO), umma::make_desc(w_lo + W0_OFF, LBO, W0_SBO), 256, 256, 2, ID_FWD, false);
+                            break;
+                        case 1:   // forward layer 1: h0 . W1^T
+                            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_H0, LBO, BX_SBO), desc(a_lo, CH_H0, LBO, BX_SBO),
+                                             umma::make_desc(w_hi + W1_OFF, LBO, W1_SBO), umma::make_desc(w_lo + W1_OFF, LBO, W1_SBO), 256, 256, 2, ID_FWD, false);
+                            break;
+                        case 2:   // forward layer 2: [enc | h1] (chunks 4..11) . W2^T
+                            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_ENC, LBO, BX_SBO), desc(a_lo, CH_ENC, LBO, BX_SBO),
+                                             umma::make_desc(w_hi + W2_OFF, LBO, W2_SBO), umma::make_desc(w_lo + W2_OFF, LBO, W2_SBO), 256, 256, 4, ID_FWD, false);
+                            break;
+                        case 3:   // backward layer 2: dW2 += G^T.[enc|h1];  d_enc = G.W2[:, :32];  dh1 = G.W2[:, 32:]
+                            umma::mma_bf16x3(tmem + T_DW2, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_ENC, BX_SBO, LBO),
+                                             desc(a_lo, CH_ENC, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW64, !first);
+                            umma::mma_bf16x3(tmem + T_DENC, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
+                                             umma::make_desc(w_hi + W2_OFF, W2_SBO, LBO), umma::make_desc(w_lo + W2_OFF, W2_SBO, LBO), 256, 2 * W2_SBO, 2, ID_DX, false);
+                            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
+                                             umma::make_desc(w_hi + W2_OFF + 4 * LBO, W2_SBO, LBO), umma::make_desc(w_lo + W2_OFF + 4 * LBO, W2_SBO, LBO), 256,
+                                             2 * W2_SBO, 2, ID_DX, false);
+                            break;
+                        case 4:   // backward layer 1: dW1 += G^T.h0;  dh0 = G.W1
+                            umma::mma_bf16x3(tmem + T_DW1, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_H0, BX_SBO, LBO),
+                                             desc(a_lo, CH_H0, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW32, !first);
+                            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
+                                             umma::make_desc(w_hi + W1_OFF, W1_SBO, LBO), umma::make_desc(w_lo + W1_OFF, W1_SBO, LBO), 256, 2 * W1_SBO, 2, ID_DX, false);
+                            break;
+                        default:  // backward layer 0: dW0 += G^T.enc;  d_enc += G.W0
+                            umma::mma_bf16x3(tmem + T_DW0, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_ENC, BX_SBO, LBO),
+                                             desc(a_lo, CH_ENC, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW32, !first);
+                            umma::mma_bf16x3(tmem + T_DENC, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
+                                             umma::make_desc(w_hi + W0_OFF, W0_SBO, LBO), umma::make_desc(w_lo + W0_OFF, W0_SBO, LBO), 256, 2 * W0_SBO, 2, ID_DX, true);
+                            break;
+                    }
+                    umma::commit(&ctl->mbar);
+                }
+                __syncwarp();
+            }
+            first = false;
+        }
+    } else {
+    // ================= the 8 epilogue warps
+    auto sync_issue = [&]() {   // operands of the next phase are written, TMEM reads of the last one are done: release the MMA warp
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        __syncthreads();
+        umma::named_bar_arrive(1, NT_B);
     };
     auto wait_mma = [&]() {
         umma::mbar_wait(&ctl->mbar, phase);
         phase ^= 1;
         umma::fence_after_sync();
     };
-    auto desc = [&](uint32_t base, uint32_t chunk, uint32_t lbo, uint32_t sbo) { return umma::make_desc(base + chunk * LBO, lbo, sbo); };
-
     // ---- deferred scatter: the gradient of the PREVIOUS tile (still in TMEM) is scattered, one slot at a time, after
     // each MMA issue of the current tile.  Thread (r, half) owns levels l = 2*li + half (even levels on half 0, odd on
     // half 1: the contended coarse levels and the all-miss fine levels are split evenly over the two halves of the CTA).
@@ -583,7 +648,6 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
     int n_st = 0;
     auto stamp = [&]() { if (stamps && n_st < 128) stamps[n_st++] = clock64(); };
 
-    const uint64_t n_tiles = (P + TILE - 1) / TILE;
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t T_DENC = (it & 1u) ? T_DENC1 : T_DENC0;
@@ -623,12 +687,6 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         // ---------------- forward layer 0
         sync_issue();
         stamp();   // 2: after the barrier
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_ENC, LBO, BX_SBO), desc(a_lo, CH_ENC, LBO, BX_SBO),
-                             umma::make_desc(w_hi + W0_OFF, LBO, W0_SBO), umma::make_desc(w_lo + W0_OFF, LBO, W0_SBO), 256, 256, 2, ID_FWD, false);
-            umma::commit(&ctl->mbar);
-        }
         if (do_scatter) { scatter_slot(0); scatter_slot(1); }
         stamp();
         wait_mma();
@@ -640,12 +698,6 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         store_half_row(A_hi, A_lo, r, CH_H0, half, BX_SBO, v);
         // ---------------- forward layer 1
         sync_issue();
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_H0, LBO, BX_SBO), desc(a_lo, CH_H0, LBO, BX_SBO),
-                             umma::make_desc(w_hi + W1_OFF, LBO, W1_SBO), umma::make_desc(w_lo + W1_OFF, LBO, W1_SBO), 256, 256, 2, ID_FWD, false);
-            umma::commit(&ctl->mbar);
-        }
         if (do_scatter) { scatter_slot(2); }
         stamp();
         wait_mma();
@@ -657,12 +709,6 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         store_half_row(A_hi, A_lo, r, CH_H1, half, BX_SBO, v);
         // ---------------- forward layer 2: [enc | h1] (chunks 4..11) . W2^T
         sync_issue();
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_ENC, LBO, BX_SBO), desc(a_lo, CH_ENC, LBO, BX_SBO),
-                             umma::make_desc(w_hi + W2_OFF, LBO, W2_SBO), umma::make_desc(w_lo + W2_OFF, LBO, W2_SBO), 256, 256, 4, ID_FWD, false);
-            umma::commit(&ctl->mbar);
-        }
         if (do_scatter) { scatter_slot(3); }
         stamp();
         wait_mma();
@@ -678,13 +724,13 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
             part = __fmaf_rn(h2[i], small->w3[16 * half + i], part);
         }
         if (half == 1) xchg[r] = part;
-        __syncthreads();
+        umma::named_bar_sync(2, NT);
         if (half == 0) {
             const float s = (part + xchg[r]) + small->b3;
             const float y = head_activation(s, mp.head);
             xchg2[r] = dsig * head_derivative(s, y, mp.head);
         }
-        __syncthreads();
+        umma::named_bar_sync(2, NT);
         const float gpre = xchg2[r];
         {
             float gw3[16];
@@ -701,17 +747,6 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         store_half_row(A_hi, A_lo, r, CH_G, half, BX_SBO, v);
         // ---------------- backward layer 2: dW2 += G^T.[enc|h1];  d_enc = G.W2[:, :32];  dh1 = G.W2[:, 32:]
         sync_issue();
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::mma_bf16x3(tmem + T_DW2, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_ENC, BX_SBO, LBO),
-                             desc(a_lo, CH_ENC, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW64, !first_tile);
-            umma::mma_bf16x3(tmem + T_DENC, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
-                             umma::make_desc(w_hi + W2_OFF, W2_SBO, LBO), umma::make_desc(w_lo + W2_OFF, W2_SBO, LBO), 256, 2 * W2_SBO, 2, ID_DX, false);
-            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
-                             umma::make_desc(w_hi + W2_OFF + 4 * LBO, W2_SBO, LBO), umma::make_desc(w_lo + W2_OFF + 4 * LBO, W2_SBO, LBO), 256,
-                             2 * W2_SBO, 2, ID_DX, false);
-            umma::commit(&ctl->mbar);
-        }
         if (do_scatter) { scatter_slot(4); }
         stamp();
         wait_mma();
@@ -728,14 +763,6 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         store_half_row(A_hi, A_lo, r, CH_G, half, BX_SBO, v);
         // ---------------- backward layer 1: dW1 += G^T.h0;  dh0 = G.W1
         sync_issue();
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::mma_bf16x3(tmem + T_DW1, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_H0, BX_SBO, LBO),
-                             desc(a_lo, CH_H0, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW32, !first_tile);
-            umma::mma_bf16x3(tmem + T_S, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
-                             umma::make_desc(w_hi + W1_OFF, W1_SBO, LBO), umma::make_desc(w_lo + W1_OFF, W1_SBO, LBO), 256, 2 * W1_SBO, 2, ID_DX, false);
-            umma::commit(&ctl->mbar);
-        }
         if (do_scatter) { scatter_slot(5); }
         stamp();
         wait_mma();
@@ -752,14 +779,6 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         store_half_row(A_hi, A_lo, r, CH_G, half, BX_SBO, v);
         // ---------------- backward layer 0: dW0 += G^T.enc;  d_enc += G.W0
         sync_issue();
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::mma_bf16x3(tmem + T_DW0, desc(a_hi, CH_G, BX_SBO, LBO), desc(a_lo, CH_G, BX_SBO, LBO), desc(a_hi, CH_ENC, BX_SBO, LBO),
-                             desc(a_lo, CH_ENC, BX_SBO, LBO), 2 * BX_SBO, 2 * BX_SBO, 8, ID_DW32, !first_tile);
-            umma::mma_bf16x3(tmem + T_DENC, desc(a_hi, CH_G, LBO, BX_SBO), desc(a_lo, CH_G, LBO, BX_SBO),
-                             umma::make_desc(w_hi + W0_OFF, W0_SBO, LBO), umma::make_desc(w_lo + W0_OFF, W0_SBO, LBO), 256, 2 * W0_SBO, 2, ID_DX, true);
-            umma::commit(&ctl->mbar);
-        }
         if (do_scatter) { scatter_slot(6); scatter_slot(7); }
         stamp();
         wait_mma();
@@ -770,24 +789,26 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         have_prev = true;
         tdenc_prev = tmem + lane_base + T_DENC;
         first_tile = false;
-        umma::fence_before_sync();
-        __syncthreads();
     }
     if (do_scatter) {   // the last tile of this CTA
 #pragma unroll 1
         for (int slot = 0; slot < 8; ++slot) scatter_slot(slot);
     }
-
-    // ================= flush the MLP gradients of this CTA into its slot of the partials workspace
-    float *mine = partials + (size_t)blockIdx.x * PTOTAL;
-    const bool did_work = blockIdx.x < n_tiles;
-    // SIMT-side sums: every warp holds partial column sums over its 32 rows; combine the 4 warps of each half
+    // SIMT-side sums: every warp holds partial column sums over its 32 rows
     wred[warp * 80 + 0 * 16 + colsum_index(lane)] = acc_db2;   // lanes l and l^1 hold the same column: benign duplicate store
     wred[warp * 80 + 1 * 16 + colsum_index(lane)] = acc_db1;
     wred[warp * 80 + 2 * 16 + colsum_index(lane)] = acc_db0;
     wred[warp * 80 + 3 * 16 + colsum_index(lane)] = acc_dw3;
     if (lane == 0) wred[warp * 80 + 64] = acc_db3;
+    umma::fence_before_sync();
+    }   // epilogue warps
+
+    // ================= flush the MLP gradients of this CTA into its slot of the partials workspace
+    float *mine = partials + (size_t)blockIdx.x * PTOTAL;
+    const bool did_work = blockIdx.x < n_tiles;
     __syncthreads();
+    umma::fence_after_sync();
+    // combine the per-warp column sums of the 4 warps of each half
     if (t < 32) {   // column j of the 32-wide vectors: half = j / 16 -> warps 4*half .. 4*half+3
         const int hj = t >> 4, cj = t & 15;
         float s2 = 0.f, s1 = 0.f, s0 = 0.f, sw = 0.f;
@@ -804,7 +825,7 @@ __global__ void __launch_bounds__(NT, 2) k_density_bwd_tc(const GridParams gp, c
         }
     }
     // tensor-core side: dW_l[o][k] sits in TMEM lane o (0..31) -> warps 0 and 4 read it (16 columns at a time)
-    if ((warp & 3) == 0) {
+    if ((warp & 3) == 0 && warp < 8) {
         float w16[16];
         auto dump = [&](uint32_t tcol, int dst, int ldw, int ncols) {
             for (int c0 = 16 * half; c0 < ncols; c0 += 32) {
@@ -883,7 +904,7 @@ static int launch_bwd_tc_t(const GridParams &gp, const nafb_mlp &mp, const Sampl
         if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): %s", cudaGetErrorString(e));
         configured = true;
     }
-    k_density_bwd_tc<SRC, C><<<grid, NT, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, nafb_debug_flags());
+    k_density_bwd_tc<SRC, C><<<grid, NT_B, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, nafb_debug_flags());
     NAFB_CHECK_LAUNCH("density_backward(tc)");
     return NAFB_OK;
 }

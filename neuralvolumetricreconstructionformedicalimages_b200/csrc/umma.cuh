@@ -88,6 +88,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
         : "memory");
 }
 
+// ---- named barriers (producer / consumer hand-off between warp roles): `threads` = arriving + syncing threads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ---- tensor memory
 // one full warp: allocate `ncols` (power of two >= 32) columns, base address written to *slot (smem)
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {

@@ -104,10 +104,15 @@ class NAFEngine:
     # ------------------------------------------------------------------ flat parameter vector
     def _flatten(self):
         params = [self.net.encoder.embeddings] + self.net.flat_params()
-        offs, n = [], 0
+        # Lead-in of 2 floats: the table starts 8 bytes past a 16-byte boundary.  Every hashed level of the shipped grids
+        # starts at an ODD entry offset (4913 + 35937 + 274625 + k * 2^19), so its entry pairs (2k, 2k+1) -- the x-neighbour
+        # pairs of the xor hash -- land on 16-byte boundaries and the kernels serve them with one 128-bit access
+        # (common.cuh load_entry_pair / red_add_entry_pair; they test the alignment at run time, so any base is correct).
+        offs, n = [], 2
         for p in params:
             offs.append(n)
-            n += _round_up(p.numel(), 4)  # every tensor starts on a 16-byte boundary
+            n += _round_up(p.numel(), 4)
+        n = _round_up(n, 4)
         self.flat_param = torch.zeros(n, device=self.device, dtype=torch.float32)
         self.flat_grad = torch.zeros_like(self.flat_param)
         self.exp_avg = torch.zeros_like(self.flat_param)
