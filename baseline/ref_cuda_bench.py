@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Time the REFERENCE's own CUDA build of the NAF training step on this GPU (the denominator of BASELINE.json's
+">= 20x the reference's CUDA build" target).  Needs baseline/_ref/ (see baseline/stage_ref.sh; git-ignored, built in the
+container that mounts /root/reference, shipped to the GPU box with the repository snapshot).
+
+Runs the reference's render / DensityNetwork / HashEncoder / calc_mse_loss + torch.optim.Adam, unmodified except for the
+2-line `.scalar_type()` compile fix, on the same synthetic chest_50 workload as bench.py, two ways:
+  chunked   : train.py:69-127 as intended (200-ray chunks, masked MSE per chunk, coords slice corrected)
+  one_call  : one render() call per step (best case for the reference)
+Prints one JSON line per variant.  None of this repository's kernels are on that path.
+"""
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.path.join(HERE, "_ref")
+
+
+def import_reference():
+    if not os.path.isdir(os.path.join(REF, "src")):
+        raise SystemExit("baseline/_ref/src is missing: run baseline/stage_ref.sh where /root/reference is mounted")
+    for name in ["matplotlib", "matplotlib.pyplot", "open3d", "skimage", "skimage.metrics", "imageio", "imageio.v2"]:
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["skimage.metrics"].structural_similarity = lambda *a, **k: 0.0
+    # the staged copy's JIT loader -> the pre-built extension
+    so = [f for f in os.listdir(os.path.join(REF, "build")) if f.endswith(".so")]
+    if not so:
+        raise SystemExit("baseline/_ref/build has no pre-built _hash_encoder .so")
+    spec = importlib.util.spec_from_file_location("_hash_encoder", os.path.join(REF, "build", so[0]))
+    ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ext)
+    backend = types.ModuleType("src.encoder.hashencoder.backend")
+    backend._backend = ext
+    sys.path.insert(0, REF)
+    sys.modules["src.encoder.hashencoder.backend"] = backend
+    from src.encoder import get_encoder
+    from src.loss import calc_mse_loss
+    from src.network import get_network
+    from src.render import render
+    return get_encoder, get_network, render, calc_mse_loss
+
+
+def main():
+    steps = int(os.environ.get("REF_STEPS", "30"))
+    warmup = int(os.environ.get("REF_WARMUP", "5"))
+    get_encoder, get_network, render, calc_mse_loss = import_reference()
+    sys.path.insert(0, ROOT)
+    import bench
+    dev = torch.device("cuda", 0)
+    rays_b, projs_b, mask_b, _ = bench.synthetic_batches(steps + warmup, dev, seed=1234)
+    mask_b = mask_b.bool()
+    for variant in ("chunked", "one_call"):
+        torch.manual_seed(0)
+        enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
+        net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999))
+        kw = dict(n_samples=bench.N_SAMPLES, n_fine=0, perturb=True, netchunk=409600, raw_noise_std=0.0)
+
+        def step(i):
+            rays, projs, mask = rays_b[i], projs_b[i], mask_b[i]
+            opt.zero_grad()
+            loss = {"loss": 0.0}
+            if variant == "chunked":
+                for c0 in range(0, rays.shape[0], bench.LOSS_CHUNK):            # train.py:69
+                    sl = slice(c0, c0 + bench.LOSS_CHUNK)
+                    ret = render(rays[sl], net, None, chunk_size=bench.LOSS_CHUNK, **kw)
+                    m = mask[sl]
+                    calc_mse_loss(loss, projs[sl][m], ret["acc"][m])             # train.py:127
+            else:
+                ret = render(rays, net, None, **kw)
+                calc_mse_loss(loss, projs[mask], ret["acc"][mask])
+            loss["loss"].backward()
+            opt.step()
+            return loss["loss"]
+
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            l = step(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        print(json.dumps({"impl": "reference_cuda", "variant": variant, "ms_per_step": ms,
+                          "value": bench.N_RAYS * bench.N_SAMPLES / (ms * 1e-3), "unit": "samples/s", "steps": steps, "warmup": warmup,
+                          "final_loss": float(l.item()), "gpu": torch.cuda.get_device_name(0),
+                          "workload": bench.WORKLOAD}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

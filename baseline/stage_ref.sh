@@ -1,0 +1,34 @@
+#!/usr/bin/env bash
+# Stage the UNMODIFIED reference under baseline/_ref/ (git-ignored; it travels to the GPU box with the snapshot) and
+# pre-build its CUDA hash encoder for sm_100a, so that `baseline/ref_cuda_bench.py` can time the reference's own CUDA
+# build on the B200 -- the denominator of BASELINE.json's ">= 20x the reference's CUDA build" target.
+#
+# The only change applied to the staged copy is the 2-line fix without which the extension does not compile on
+# torch >= 2.1: `.type()` -> `.scalar_type()` at hashencoder.cu:393,424.
+# Nothing under baseline/_ref/ is ever committed or imported by the product package or by bench.py's own arm.
+set -euo pipefail
+REF_ROOT="${REF_ROOT:-/root/reference}"
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/_ref"
+if [ ! -d "$REF_ROOT/src" ]; then echo "stage_ref.sh: $REF_ROOT not mounted -- skipping" >&2; exit 0; fi
+mkdir -p "$OUT"
+rm -rf "$OUT/src"
+cp -r "$REF_ROOT/src" "$OUT/src"
+cp "$REF_ROOT/train.py" "$OUT/train.py"
+CU="$OUT/src/encoder/hashencoder/src/hashencoder.cu"
+sed -i 's/inputs\.type()/inputs.scalar_type()/; s/grad\.type()/grad.scalar_type()/' "$CU"
+grep -n "scalar_type()" "$CU"
+# pre-build (nvcc cross-compiles without a GPU); the JIT loader of the staged copy is replaced at import time by
+# baseline/ref_cuda_bench.py, which loads this .so instead of compiling on the GPU box
+python - <<PY
+import os, torch
+os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+from torch.utils.cpp_extension import load
+src = "$OUT/src/encoder/hashencoder/src"
+bd = "$OUT/build"
+os.makedirs(bd, exist_ok=True)
+m = load(name="_hash_encoder", extra_cflags=["-O3"],
+         extra_cuda_cflags=["-O3", "-U__CUDA_NO_HALF_OPERATORS__", "-U__CUDA_NO_HALF_CONVERSIONS__", "-U__CUDA_NO_HALF2_OPERATORS__"],
+         sources=[os.path.join(src, f) for f in ["hashencoder.cu", "bindings.cpp"]], build_directory=bd, verbose=False)
+print("built", m.__file__)
+PY

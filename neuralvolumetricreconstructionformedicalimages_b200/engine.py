@@ -260,13 +260,9 @@ class NAFEngine:
         Returns a tensor [(i1-i0), n2, n3]."""
         n1, n2, n3 = [int(v) for v in n_voxel]
         i0, i1 = (0, n1) if slab is None else (int(slab[0]), int(slab[1]))
-        res = density_forward(self.meta, self.table, self.mlp_params,
+        res = density_forward(self.meta, self.table, self.mlp_params, sigma_out=out,
                               voxels=(n1, n2, n3, i0, i1, float(s_half[0]), float(s_half[1]), float(s_half[2])))
-        sig = res["sigma"].view(i1 - i0, n2, n3)
-        if out is not None:
-            out.copy_(sig)
-            return out
-        return sig
+        return res["sigma"].view(i1 - i0, n2, n3)
 
     def rank_slab(self, n1):
         """[i0, i1) of the outermost voxel index owned by this rank."""

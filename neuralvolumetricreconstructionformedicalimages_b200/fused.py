@@ -75,7 +75,8 @@ def stash_bytes(meta: NetMeta, table, params, n_points: int) -> int:
 
 
 def density_forward(meta: NetMeta, table, params, *, pts=None, rays=None, t_rand=None, n_samples=0, perturb=False,
-                    voxels=None, want_acc=False, want_pts=False, want_z=False, want_sigma=True, flags=None, want_stash=False):
+                    voxels=None, want_acc=False, want_pts=False, want_z=False, want_sigma=True, flags=None, want_stash=False,
+                    sigma_out=None):
     """Low-level launcher shared by the autograd functions and the engine. Returns dict of outputs."""
     L_ = _lib.lib()
     dev = table.device
@@ -97,7 +98,12 @@ def density_forward(meta: NetMeta, table, params, *, pts=None, rays=None, t_rand
         P = (i1 - i0) * n2 * n3
         smp = meta.sampler(n1=n1, n2=n2, n3=n3, i0=i0, i1=i1, s1=s1, s2=s2, s3=s3)
         src = _lib.SRC_VOXELS
-    sigma = torch.empty(P, device=dev, dtype=torch.float32) if want_sigma else None
+    if sigma_out is not None:
+        if sigma_out.numel() != P or sigma_out.dtype != torch.float32 or not sigma_out.is_contiguous() or sigma_out.device != dev:
+            raise RuntimeError("sigma_out must be a contiguous float32 tensor of P elements on the table's device")
+        sigma = sigma_out.view(-1)
+    else:
+        sigma = torch.empty(P, device=dev, dtype=torch.float32) if want_sigma else None
     acc = torch.zeros(rays.shape[0], device=dev, dtype=torch.float32) if want_acc else None
     z = torch.empty(rays.shape[0], n_samples, device=dev, dtype=torch.float32) if want_z else None
     po = torch.empty(rays.shape[0], n_samples, 3, device=dev, dtype=torch.float32) if want_pts else None
