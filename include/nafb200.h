@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 2
+#define NAFB_ABI_VERSION 3
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -179,6 +179,45 @@ int nafb_mse_loss(float *pred, const float *target, const uint8_t *mask, uint32_
 int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float lr,
                    float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad,
                    nafb_stream_t stream);
+
+/* ------------------------------------------------------------------ multi-GPU exchange step
+ * The reference has no distributed code; the engine shards rays over ranks and needs ONE
+ * exchange per iteration: sum the flat gradient over ranks, Adam, identical parameters everywhere.
+ * nafb_adam_exchange_step does all of it in one kernel over NVLink peer memory: rank r owns the slice
+ * nafb_exchange_slice(n, r, W) of the flat vector, loads that slice of every rank's gradient (P2P), adds them in rank
+ * order, applies Adam (state for the slice only) and stores the new parameters into every rank's replica.
+ *
+ * Buffers that peers touch (parameters, gradients, flag blocks) must come from nafb_peer_alloc (cudaMalloc + CUDA IPC
+ * handle, zero-filled); a peer maps them with nafb_peer_open(handle).  Flag block: NAFB_XFLAG_WORDS uint32, zero before
+ * the first step.  Gradients are double buffered by the caller: `grad[w]` = this step's buffer of rank w,
+ * `grad_zero` = the LOCAL buffer of the other parity (cleared by the kernel; NULL to skip).  `step` (1-based, strictly
+ * increasing, the same on every rank) doubles as the synchronisation epoch.  A lost peer raises flag word
+ * NAFB_XFLAG_ERROR of the local block after a bounded spin instead of hanging the GPU. */
+#define NAFB_MAX_RANKS 8
+#define NAFB_XFLAG_ARRIVE 0   /* [0..7]  written by rank i: "my gradient of this epoch is complete"            */
+#define NAFB_XFLAG_DONE 8     /* [8..15] written by rank i: "I have finished writing your parameters"          */
+#define NAFB_XFLAG_ERROR 16   /* != 0: a spin timed out (value - 1 = index of the flag that never arrived)     */
+#define NAFB_XFLAG_TICKET 17  /* local block counter                                                           */
+#define NAFB_XFLAG_WORDS 32
+
+typedef struct nafb_exchange {
+    uint32_t world, rank;
+    float *param[NAFB_MAX_RANKS];      /* every rank's flat parameters [n] (param[rank] is local)               */
+    float *grad[NAFB_MAX_RANKS];       /* every rank's flat gradient [n] of this step's parity                  */
+    uint32_t *flags[NAFB_MAX_RANKS];   /* every rank's flag block [NAFB_XFLAG_WORDS]                            */
+    float *grad_zero;                  /* local gradient buffer of the other parity, or NULL                    */
+    float *exp_avg, *exp_avg_sq;       /* LOCAL, slice-sized: [i1 - i0] of nafb_exchange_slice(n, rank, world)  */
+    uint64_t n;                        /* floats, multiple of 4                                                 */
+} nafb_exchange;
+
+int nafb_peer_alloc(uint64_t bytes, void **ptr, unsigned char *handle64);
+int nafb_peer_open(const unsigned char *handle64, void **ptr);
+int nafb_peer_close(void *ptr);
+int nafb_peer_free(void *ptr);
+/* [i0, i1) in floats (multiples of 4) of the slice rank `rank` owns */
+int nafb_exchange_slice(uint64_t n, uint32_t rank, uint32_t world, uint64_t *i0, uint64_t *i1);
+int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float beta2, float eps, uint32_t step,
+                            float grad_scale, nafb_stream_t stream);
 
 /* Arithmetic of the fused density kernels: 0 (default) = tcgen05 tensor cores with bf16x3 split
  * operands and fp32 TMEM accumulation wherever the configuration allows (4 x 32 MLP, skip at 2),

@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnafb200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NAFB_MAX_LEVELS = 32
 NAFB_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
@@ -49,7 +49,24 @@ class Sampler(ctypes.Structure):
                 ("bound", ctypes.c_float), ("clamp", ctypes.c_float)]
 
 
+NAFB_MAX_RANKS = 8
+XFLAG_ARRIVE, XFLAG_DONE, XFLAG_ERROR, XFLAG_TICKET, XFLAG_WORDS = 0, 8, 16, 17, 32
+
+
+class Exchange(ctypes.Structure):
+    _fields_ = [("world", u32), ("rank", u32), ("param", ctypes.c_void_p * NAFB_MAX_RANKS), ("grad", ctypes.c_void_p * NAFB_MAX_RANKS),
+                ("flags", ctypes.c_void_p * NAFB_MAX_RANKS), ("grad_zero", ctypes.c_void_p), ("exp_avg", ctypes.c_void_p),
+                ("exp_avg_sq", ctypes.c_void_p), ("n", u64)]
+
+
 _SIGNATURES = {
+    "nafb_peer_alloc": (ctypes.c_int, [u64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "nafb_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "nafb_peer_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "nafb_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "nafb_exchange_slice": (ctypes.c_int, [u64, u32, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
+    "nafb_adam_exchange_step": (ctypes.c_int, [ctypes.POINTER(Exchange), ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, u32,
+                                               ctypes.c_float, ctypes.c_void_p]),
     "nafb_abi_version": (ctypes.c_int, []),
     "nafb_last_error": (ctypes.c_char_p, []),
     "nafb_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
@@ -127,6 +144,49 @@ def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
 
 def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class RawCudaBuffer:
+    """A device allocation owned by the library (nafb_peer_alloc), exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int, handle: bytes = b"", owner: bool = True):
+        self.ptr, self.nbytes, self.handle, self.owner = int(ptr), int(nbytes), handle, owner
+
+    def tensor(self, byte_offset: int, numel: int, dtype, device):
+        item = torch.empty(0, dtype=dtype).element_size()
+        assert byte_offset % item == 0 and byte_offset + numel * item <= self.nbytes
+        typestr = {torch.float32: "<f4", torch.uint32: "<u4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (self.ptr + byte_offset, False), "version": 2}
+
+        t = torch.as_tensor(_View(), device=device)
+        t._nafb_keepalive = self
+        return t
+
+    def release(self):
+        if self.ptr:
+            (lib().nafb_peer_free if self.owner else lib().nafb_peer_close)(ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+def peer_alloc(nbytes: int) -> RawCudaBuffer:
+    p = ctypes.c_void_p()
+    h = ctypes.create_string_buffer(64)
+    check(lib().nafb_peer_alloc(int(nbytes), ctypes.byref(p), h))
+    return RawCudaBuffer(p.value, nbytes, h.raw, owner=True)
+
+
+def peer_open(handle: bytes, nbytes: int) -> RawCudaBuffer:
+    p = ctypes.c_void_p()
+    check(lib().nafb_peer_open(ctypes.c_char_p(handle), ctypes.byref(p)))
+    return RawCudaBuffer(p.value, nbytes, handle, owner=False)
+
+
+def exchange_slice(n: int, rank: int, world: int):
+    i0, i1 = u64(), u64()
+    check(lib().nafb_exchange_slice(int(n), int(rank), int(world), ctypes.byref(i0), ctypes.byref(i1)))
+    return int(i0.value), int(i1.value)
 
 
 def make_grid(table: torch.Tensor, offsets_np: np.ndarray, D: int, C: int, H: int) -> Grid:

@@ -1,0 +1,253 @@
+// exchange.cu -- the multi-GPU exchange step of NAF training as ONE kernel over NVLink peer memory:
+//
+//      reduce-scatter of the flat gradient  +  dense Adam on the owned slice  +  all-gather of the new parameters
+//
+// Every rank owns a contiguous slice of the flat parameter vector (and keeps Adam's exp_avg / exp_avg_sq for that slice
+// only).  For its slice a rank LOADS the gradient of all W ranks straight from their HBM (P2P over NVLink / NVSwitch),
+// adds them in rank order, applies Adam and STORES the new parameters into all W replicas.  Per rank that is
+// (W-1)/W * n * 4 bytes in and the same out -- the minimum an all-reduce moves -- with the optimizer's HBM traffic divided
+// by W and no separate collective launches: the transfer overlaps the arithmetic element by element.
+//
+// (What it replaces: NCCL all-reduce of 57 MB, then the dense Adam pass of adam.cu over 456 MB of HBM traffic.)
+//
+// Synchronisation is by epoch flags in peer memory (epoch = optimizer step, strictly increasing):
+//   arrive[r]  rank r's gradient of this epoch is complete (its backward kernels have finished: stream order) and it no
+//              longer reads its parameters -> peers may read r's gradient and overwrite r's parameters;
+//   done[r]    rank r has finished writing everybody's parameters (and reading everybody's gradient).
+// The kernel ends only after it has seen done[*] of every peer, so the next forward pass (stream order) sees complete
+// parameters.  Gradients are double buffered by step parity: the buffer the peers read in step s is cleared by its owner
+// in step s+1 (after the arrive barrier of s+1 nobody can still be reading it), the backward pass of s+1 accumulates into
+// the other one.  Replicas stay bit-identical by construction: each parameter is computed once, by its owner.
+//
+// Spins are bounded (NAFB_EXCHANGE_TIMEOUT_NS of %globaltimer): on expiry the kernel raises the error word of the local
+// flag block and carries on, so a lost peer cannot hang the GPU.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXR = NAFB_MAX_RANKS;
+constexpr unsigned long long TIMEOUT_NS = 4000000000ull;   // 4 s
+
+struct AdamConst {
+    float w1, beta2, w2, bc2_sqrt, eps, neg_step, gscale;
+};
+
+__device__ __forceinline__ void adam_one(float &p, const float g, float &m, float &v, const AdamConst &c) {
+    const float gg = __fmul_rn(g, c.gscale);
+    m = __fmaf_rn(c.w1, __fsub_rn(gg, m), m);
+    v = __fmul_rn(v, c.beta2);
+    v = __fmaf_rn(__fmul_rn(c.w2, gg), gg, v);
+    const float dn = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
+    p = __fmaf_rn(c.neg_step, __fdiv_rn(m, dn), p);
+}
+
+struct ExchangeParams {
+    uint32_t world, rank, epoch;
+    float *param[MAXR];
+    const float *grad[MAXR];
+    uint32_t *flags[MAXR];
+    float *grad_zero;
+    float *m, *v;          // slice-local
+    uint64_t n4, s0, s1;   // float4 units
+    AdamConst c;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// peer loads / stores: bypass L1 (the data lives in another GPU's memory and is never reused by this SM)
+__device__ __forceinline__ float4 ld_peer(const float4 *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_peer(float4 *p, const float4 v) { __stcg(p, v); }
+
+// wait until flag word `idx0 + w` of the LOCAL block is >= epoch for every rank w
+__device__ __forceinline__ void wait_all(const ExchangeParams &P, uint32_t idx0) {
+    if (threadIdx.x < P.world) {
+        const uint32_t *f = P.flags[P.rank] + idx0 + threadIdx.x;
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int32_t)(ld_acquire_sys(f) - P.epoch) < 0) {
+            if (globaltimer_ns() - t0 > TIMEOUT_NS) {
+                atomicExch(P.flags[P.rank] + NAFB_XFLAG_ERROR, 1u + idx0 + threadIdx.x);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+template <int W>
+__global__ void __launch_bounds__(512) k_adam_exchange(const ExchangeParams P) {
+    const uint32_t world = W > 0 ? (uint32_t)W : P.world;
+    // ---- 1. tell every rank (myself included) that my gradient is complete, then wait for everybody's
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_ARRIVE + P.rank, P.epoch);
+    }
+    wait_all(P, NAFB_XFLAG_ARRIVE);
+
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    // ---- 2. clear my gradient buffer of the other parity (its readers finished before they arrived at this epoch)
+    if (P.grad_zero) {
+        float4 *z = reinterpret_cast<float4 *>(P.grad_zero);
+        for (uint64_t i = gid; i < P.n4; i += stride) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ---- 3. my slice: sum of the W gradients (rank order), Adam, new parameters to all W replicas.
+    // U elements per thread and iteration keep U*W peer loads in flight (NVLink latency is a few microseconds).
+    constexpr int U = W == 2 ? 4 : (W == 4 ? 2 : 1);
+    float4 *m4 = reinterpret_cast<float4 *>(P.m), *v4 = reinterpret_cast<float4 *>(P.v);
+    const float4 *p_in = reinterpret_cast<const float4 *>(P.param[P.rank]);
+    for (uint64_t i0 = P.s0 + gid; i0 < P.s1; i0 += (uint64_t)U * stride) {
+        float4 g[U][MAXR], p[U], m[U], v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            if (i < P.s1) {
+#pragma unroll
+                for (int w = 0; w < MAXR; ++w)
+                    if (w < (int)world) g[u][w] = ld_peer(reinterpret_cast<const float4 *>(P.grad[w]) + i);
+                p[u] = p_in[i]; m[u] = m4[i - P.s0]; v[u] = v4[i - P.s0];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            if (i < P.s1) {
+                float4 s = g[u][0];
+#pragma unroll
+                for (int w = 1; w < MAXR; ++w)
+                    if (w < (int)world) { s.x += g[u][w].x; s.y += g[u][w].y; s.z += g[u][w].z; s.w += g[u][w].w; }
+                adam_one(p[u].x, s.x, m[u].x, v[u].x, P.c);
+                adam_one(p[u].y, s.y, m[u].y, v[u].y, P.c);
+                adam_one(p[u].z, s.z, m[u].z, v[u].z, P.c);
+                adam_one(p[u].w, s.w, m[u].w, v[u].w, P.c);
+                m4[i - P.s0] = m[u];
+                v4[i - P.s0] = v[u];
+#pragma unroll
+                for (int w = 0; w < MAXR; ++w)
+                    if (w < (int)world) st_peer(reinterpret_cast<float4 *>(P.param[w]) + i, p[u]);
+            }
+        }
+    }
+    // ---- 4. last block out: publish "done" to every rank, then wait until every rank is done with MY replica
+    __threadfence_system();
+    __syncthreads();
+    __shared__ uint32_t s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(P.flags[P.rank] + NAFB_XFLAG_TICKET, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x == 0) P.flags[P.rank][NAFB_XFLAG_TICKET] = 0u;
+    if (threadIdx.x < world) st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_DONE + P.rank, P.epoch);
+    wait_all(P, NAFB_XFLAG_DONE);
+}
+
+}  // namespace
+
+extern "C" {
+
+int nafb_peer_alloc(uint64_t bytes, void **ptr, unsigned char *handle64) {
+    if (!ptr || !handle64 || bytes == 0) NAFB_FAIL(NAFB_ERR_INVALID, "peer_alloc: bad argument");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "peer_alloc: cudaMalloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) { cudaFree(p); NAFB_FAIL(NAFB_ERR_CUDA, "peer_alloc: cudaMemset: %s", cudaGetErrorString(e)); }
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); NAFB_FAIL(NAFB_ERR_CUDA, "peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return NAFB_OK;
+}
+
+int nafb_peer_open(const unsigned char *handle64, void **ptr) {
+    if (!ptr || !handle64) NAFB_FAIL(NAFB_ERR_INVALID, "peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    *ptr = p;
+    return NAFB_OK;
+}
+
+int nafb_peer_close(void *ptr) {
+    if (!ptr) return NAFB_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "peer_close: %s", cudaGetErrorString(e));
+    return NAFB_OK;
+}
+
+int nafb_peer_free(void *ptr) {
+    if (!ptr) return NAFB_OK;
+    cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "peer_free: %s", cudaGetErrorString(e));
+    return NAFB_OK;
+}
+
+int nafb_exchange_slice(uint64_t n, uint32_t rank, uint32_t world, uint64_t *i0, uint64_t *i1) {
+    if (!i0 || !i1 || world == 0 || rank >= world || (n & 3)) NAFB_FAIL(NAFB_ERR_INVALID, "exchange_slice: bad argument (n must be a multiple of 4)");
+    const uint64_t n4 = n >> 2, base = n4 / world, extra = n4 % world;
+    const uint64_t a = rank * base + (rank < extra ? rank : extra);
+    *i0 = a << 2;
+    *i1 = (a + base + (rank < extra ? 1 : 0)) << 2;
+    return NAFB_OK;
+}
+
+int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale,
+                            nafb_stream_t stream) {
+    if (!x) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: null descriptor");
+    if (x->world < 1 || x->world > NAFB_MAX_RANKS || x->rank >= x->world) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: world %u / rank %u", x->world, x->rank);
+    if (step == 0) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: step is 1-based");
+    if (x->n == 0 || (x->n & 3)) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: n must be a positive multiple of 4");
+    if (!x->exp_avg || !x->exp_avg_sq) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: null optimizer state");
+    ExchangeParams P{};
+    P.world = x->world; P.rank = x->rank; P.epoch = step;
+    uintptr_t align = (uintptr_t)x->exp_avg | (uintptr_t)x->exp_avg_sq | (uintptr_t)x->grad_zero;
+    for (uint32_t w = 0; w < x->world; ++w) {
+        if (!x->param[w] || !x->grad[w] || !x->flags[w]) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: null pointer for rank %u", w);
+        P.param[w] = x->param[w]; P.grad[w] = x->grad[w]; P.flags[w] = x->flags[w];
+        align |= (uintptr_t)x->param[w] | (uintptr_t)x->grad[w];
+    }
+    if (align & 15) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: buffers must be 16-byte aligned");
+    P.grad_zero = x->grad_zero; P.m = x->exp_avg; P.v = x->exp_avg_sq;
+    uint64_t i0 = 0, i1 = 0;
+    int rc = nafb_exchange_slice(x->n, x->rank, x->world, &i0, &i1);
+    if (rc) return rc;
+    P.n4 = x->n >> 2; P.s0 = i0 >> 2; P.s1 = i1 >> 2;
+    const double b1 = (double)beta1, b2 = (double)beta2;
+    const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+    P.c.w1 = (float)(1.0 - b1); P.c.beta2 = beta2; P.c.w2 = (float)(1.0 - b2); P.c.bc2_sqrt = (float)sqrt(bc2); P.c.eps = eps;
+    P.c.neg_step = (float)(-((double)lr / bc1)); P.c.gscale = grad_scale;
+    // persistent grid: as many blocks of 512 threads as are resident at once (blocks spin on the arrival flags)
+    cudaStream_t s = (cudaStream_t)stream;
+    auto launch = [&](auto kernel) {
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 512, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        kernel<<<(unsigned)(nafb_sm_count() * per_sm), 512, 0, s>>>(P);
+    };
+    switch (x->world) {
+        case 2: launch(k_adam_exchange<2>); break;
+        case 4: launch(k_adam_exchange<4>); break;
+        case 8: launch(k_adam_exchange<8>); break;
+        default: launch(k_adam_exchange<0>); break;
+    }
+    NAFB_CHECK_LAUNCH("adam_exchange_step");
+    return NAFB_OK;
+}
+
+}  // extern "C"

@@ -13,8 +13,15 @@ It takes the place of ``Trainer.train_step`` (reference src/trainer.py:134-142) 
 ordinary ``nn.Parameter`` views of the flat vector, so ``state_dict()`` / ``ckpt.tar`` round-trip
 with the reference layout (encoder.embeddings, layers.i.weight/bias).
 
-Multi-GPU: one process per GPU, rays sharded across ranks, parameters/optimizer state replicated;
-the flat gradient is all-reduced (sum) with NCCL and Adam divides by world size (== DDP's mean).
+Multi-GPU: one process per GPU, rays sharded across ranks, parameters replicated.  The step's one exchange
+(sum of the flat gradient over ranks -> Adam -> identical parameters everywhere) runs in one of two ways:
+
+  exchange="peer" (default when it can be set up): ONE kernel over NVLink peer memory (csrc/exchange.cu): every rank owns a
+      slice of the flat vector, pulls that slice of all ranks' gradients (P2P loads), applies Adam (optimizer state for the
+      slice only) and pushes the new parameters into all replicas (P2P stores).  Buffers come from nafb_peer_alloc and are
+      mapped into the peers with CUDA IPC; gradients are double buffered by step parity.
+  exchange="nccl": dist.all_reduce of the flat gradient, then the dense Adam kernel with grad_scale = 1/world.
+
 The voxel query shards by slabs of the outermost index and needs no collective.
 """
 from __future__ import annotations
@@ -76,9 +83,57 @@ class EventTimer:
         return {k: (t / c, c) for k, (t, c) in acc.items()}
 
 
+class PeerExchange:
+    """Peer-mapped flat buffers of all ranks + the descriptors of nafb_adam_exchange_step (one per gradient parity)."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, n, device, group, rank, world):
+        self.n, self.rank, self.world, self.device = int(n), rank, world, device
+        nbytes = self.FLAG_BYTES + 3 * self.n * 4
+        self.local = _lib.peer_alloc(nbytes)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, self.local.handle, group=group)
+        self.bufs = [self.local if w == rank else _lib.peer_open(handles[w], nbytes) for w in range(world)]
+        fb, seg = self.FLAG_BYTES, self.n * 4
+        self.flags = self.local.tensor(0, _lib.XFLAG_WORDS, torch.int32, device)
+        self.param = self.local.tensor(fb, self.n, torch.float32, device)
+        self.grad = [self.local.tensor(fb + (1 + k) * seg, self.n, torch.float32, device) for k in (0, 1)]
+        i0, i1 = _lib.exchange_slice(self.n, rank, world)
+        self.slice = (i0, i1)
+        self.exp_avg = torch.zeros(i1 - i0, device=device, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(i1 - i0, device=device, dtype=torch.float32)
+        self.desc = []
+        for par in (0, 1):
+            x = _lib.Exchange()
+            x.world, x.rank, x.n = world, rank, self.n
+            for w, b in enumerate(self.bufs):
+                x.flags[w] = b.ptr
+                x.param[w] = b.ptr + fb
+                x.grad[w] = b.ptr + fb + (1 + par) * seg
+            x.grad_zero = self.local.ptr + fb + (1 + (1 - par)) * seg
+            x.exp_avg, x.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+            self.desc.append(x)
+        if world > 1:
+            dist.barrier(group=group)   # every rank has mapped every buffer before anybody launches
+
+    def step(self, par, lr, betas, eps, step, stream):
+        _lib.check(_lib.lib().nafb_adam_exchange_step(ctypes.byref(self.desc[par]), lr, betas[0], betas[1], eps, step, 1.0 / self.world, stream))
+
+    def error_word(self) -> int:
+        """0, or 1 + index of the peer flag a bounded spin gave up on (synchronises the stream)."""
+        return int(self.flags[_lib.XFLAG_ERROR].item())
+
+    def close(self):
+        for b in self.bufs:
+            if b is not self.local:
+                b.release()
+
+
 class NAFEngine:
     def __init__(self, net: DensityNetwork, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, n_samples=192, perturb=True, loss_chunk=None,
-                 use_cuda_graph=True, process_group=None, use_stash=True):
+                 use_cuda_graph=True, process_group=None, use_stash=True, exchange="auto"):
         meta = net.fused_meta()
         if meta is None:
             raise RuntimeError("NAFEngine needs a DensityNetwork in a fused-capable configuration "
@@ -95,14 +150,17 @@ class NAFEngine:
         self.use_stash = bool(use_stash)  # forward leaves the encodings (128 B/point) for backward instead of a second gather
         self.pg = process_group
         self.rank, self.world_size = parallel.world_info(process_group)
-        self._flatten()
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        self.px = None
+        self._flatten(exchange)
         if self.world_size > 1:   # replicas start identical
             parallel.broadcast_(self.flat_param, 0, process_group)
         self._graphs = {}
         self._static = {}
 
     # ------------------------------------------------------------------ flat parameter vector
-    def _flatten(self):
+    def _flatten(self, exchange="auto"):
         params = [self.net.encoder.embeddings] + self.net.flat_params()
         # Lead-in of 2 floats: the table starts 8 bytes past a 16-byte boundary.  Every hashed level of the shipped grids
         # starts at an ODD entry offset (4913 + 35937 + 274625 + k * 2^19), so its entry pairs (2k, 2k+1) -- the x-neighbour
@@ -113,25 +171,62 @@ class NAFEngine:
             offs.append(n)
             n += _round_up(p.numel(), 4)
         n = _round_up(n, 4)
-        self.flat_param = torch.zeros(n, device=self.device, dtype=torch.float32)
-        self.flat_grad = torch.zeros_like(self.flat_param)
-        self.exp_avg = torch.zeros_like(self.flat_param)
-        self.exp_avg_sq = torch.zeros_like(self.flat_param)
-        self._views, self._grad_views = [], []
+        want_peer = exchange == "peer" or (exchange == "auto" and self.world_size > 1)
+        if want_peer:
+            ok = 1
+            try:
+                if self.world_size > _lib.NAFB_MAX_RANKS:
+                    raise RuntimeError(f"peer exchange supports up to {_lib.NAFB_MAX_RANKS} ranks")
+                with torch.cuda.device(self.device):
+                    self.px = PeerExchange(n, self.device, self.pg, self.rank, self.world_size)
+            except Exception as e:  # CUDA IPC unavailable (container / topology): every rank must take the same decision
+                if exchange == "peer" and self.world_size == 1:
+                    raise
+                self._peer_error, ok, self.px = str(e), 0, None
+            if self.world_size > 1:
+                t = torch.tensor([ok], device=self.device, dtype=torch.int32)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.pg)
+                if int(t.item()) == 0:
+                    if exchange == "peer":
+                        raise RuntimeError("peer exchange could not be set up on every rank: " + getattr(self, "_peer_error", "failed on a peer"))
+                    if self.px is not None:
+                        self.px.close()
+                    self.px = None
+        if self.px is not None:
+            self.flat_param = self.px.param
+            self.flat_grads = self.px.grad                     # double buffered by step parity
+            self.exp_avg, self.exp_avg_sq = self.px.exp_avg, self.px.exp_avg_sq   # slice-local
+        else:
+            self.flat_param = torch.zeros(n, device=self.device, dtype=torch.float32)
+            self.flat_grads = [torch.zeros_like(self.flat_param)]
+            self.exp_avg = torch.zeros_like(self.flat_param)
+            self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self.flat_grad = self.flat_grads[0]
+        self._views = []
+        self._grad_views = [[] for _ in self.flat_grads]
         for p, o in zip(params, offs):
             v = self.flat_param[o:o + p.numel()].view_as(p)
             v.copy_(p.data)
             p.data = v  # the module's parameters now alias the flat vector
             self._views.append(v)
-            self._grad_views.append(self.flat_grad[o:o + p.numel()].view_as(p))
+            for k, fg in enumerate(self.flat_grads):
+                self._grad_views[k].append(fg[o:o + p.numel()].view_as(p))
         self.n_params = n
         self.table = self._views[0]
         self.mlp_params = self._views[1:]
-        self.grad_table = self._grad_views[0]
-        self.grad_mlp = self._grad_views[1:]
+        self.grad_table = self._grad_views[0][0]
+        self.grad_mlp = self._grad_views[0][1:]
+
+    @property
+    def exchange_mode(self):
+        return "peer" if self.px is not None else ("nccl" if self.world_size > 1 else "local")
+
+    def _parity(self):
+        """Which gradient buffer the coming step accumulates into (peer exchange: alternates; otherwise always 0)."""
+        return (self.step_count & 1) if self.px is not None else 0
 
     # ------------------------------------------------------------------ one training step
-    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None, stash=None):
+    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None, stash=None, par=0):
         L_ = _lib.lib()
         tm = timer or _NoTimer()
         N = rays.shape[0]
@@ -148,13 +243,23 @@ class NAFEngine:
         with tm("mse_loss"):
             _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), 1, st))
         with tm("density_bwd"):
-            density_backward(self.meta, self.table, self.mlp_params, dacc, self.grad_table, self.grad_mlp, rays=rays, t_rand=t_rand,
+            gv = self._grad_views[par]
+            density_backward(self.meta, self.table, self.mlp_params, dacc, gv[0], gv[1:], rays=rays, t_rand=t_rand,
                              n_samples=self.n_samples, perturb=self.perturb, stash=stash)
 
-    def _adam(self, timer=None):
+    def _exchange_and_adam(self, par, timer=None):
+        """The step's exchange + optimizer: peer kernel, or (NCCL all-reduce +) the dense Adam kernel."""
         L_ = _lib.lib()
+        tm = timer or _NoTimer()
         self.step_count += 1
-        with (timer or _NoTimer())("adam"):
+        if self.px is not None:
+            with tm("adam_exchange"):
+                self.px.step(par, self.lr, self.betas, self.eps, self.step_count, _lib.stream_ptr())
+            return
+        if self.world_size > 1:
+            with tm("all_reduce"):
+                parallel.allreduce_sum_(self.flat_grad, self.pg)
+        with tm("adam"):
             _lib.check(L_.nafb_adam_step(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
                                          _lib.ptr(self.exp_avg_sq), self.n_params, self.lr, self.betas[0], self.betas[1], self.eps,
                                          self.step_count, 1.0 / self.world_size, 1, _lib.stream_ptr()))
@@ -177,11 +282,9 @@ class NAFEngine:
                         s["t_rand"].uniform_(0.0, 1.0)
                     else:
                         s["t_rand"].copy_(t_rand)
-            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], timer, stash=s["stash"])
-            if self.world_size > 1:
-                with timer("all_reduce"):
-                    parallel.allreduce_sum_(self.flat_grad, self.pg)
-            self._adam(timer)
+            par = self._parity()
+            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], timer, stash=s["stash"], par=par)
+            self._exchange_and_adam(par, timer)
         return s["loss"][0]
 
     def _get_static(self, N, with_mask):
@@ -213,14 +316,15 @@ class NAFEngine:
                     s["t_rand"].uniform_(0.0, 1.0)  # on-device Philox, same distribution as torch.rand (render.py:99)
                 else:
                     s["t_rand"].copy_(t_rand, non_blocking=True)
-            self._run_fwd_bwd(s, (N, mask is not None))
-            parallel.allreduce_sum_(self.flat_grad, self.pg)
-            self._adam()
+            par = self._parity()
+            self._run_fwd_bwd(s, (N, mask is not None, par), par)
+            self._exchange_and_adam(par)
         return s["loss"][0]
 
-    def _run_fwd_bwd(self, s, key):
+    def _run_fwd_bwd(self, s, key, par):
+        args = (s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"])
         if not self.use_cuda_graph:
-            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], stash=s["stash"])
+            self._step_kernels(*args, stash=s["stash"], par=par)
             return
         g = self._graphs.get(key)
         if g is None:
@@ -228,12 +332,12 @@ class NAFEngine:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], stash=s["stash"])
-                self.flat_grad.zero_()  # the gradient is zero between steps (Adam clears it)
+                self._step_kernels(*args, stash=s["stash"], par=par)
+                self.flat_grads[par].zero_()  # the gradient is zero between steps (the optimizer kernel clears it)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], stash=s["stash"])
+                self._step_kernels(*args, stash=s["stash"], par=par)
             self._graphs[key] = g
             # capture does not execute: replay below performs the first real step
         g.replay()
@@ -269,11 +373,27 @@ class NAFEngine:
         return parallel.shard_range(n1, self.rank, self.world_size)
 
     # ------------------------------------------------------------------ optimizer state (ckpt compatibility)
+    def _full_state(self, t):
+        """exp_avg / exp_avg_sq as a full-length vector (peer exchange keeps only the owned slice per rank)."""
+        if self.px is None:
+            return t.clone()
+        full = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
+        i0, i1 = self.px.slice
+        full[i0:i1] = t
+        if self.world_size > 1:
+            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.pg)   # slices are disjoint
+        return full
+
     def optimizer_state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "lr": self.lr}
+        return {"step": self.step_count, "exp_avg": self._full_state(self.exp_avg), "exp_avg_sq": self._full_state(self.exp_avg_sq),
+                "lr": self.lr}
 
     def load_optimizer_state_dict(self, sd):
         self.step_count = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        i0, i1 = self.px.slice if self.px is not None else (0, self.n_params)
+        self.exp_avg.copy_(sd["exp_avg"][i0:i1])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"][i0:i1])
         self.lr = float(sd.get("lr", self.lr))
+        if self.px is not None:   # the parity of step_count selects the gradient buffer: both must be clean
+            for g in self.flat_grads:
+                g.zero_()

@@ -1,0 +1,154 @@
+"""The fused exchange kernel (reduce-scatter + Adam + all-gather over NVLink peer memory, csrc/exchange.cu).
+
+  * one GPU (world 1, flags and "peers" are the local buffers): bit-exact against the dense Adam kernel, which is itself
+    pinned against torch.optim.Adam (test_gpu_parity.py::test_adam_matches_torch); gradient double buffering; flags;
+  * NAFEngine(exchange="peer") on one GPU trains like the default engine;
+  * two GPUs (skipped when the box has one): two ranks over NCCL + CUDA IPC; the peer path keeps the replicas
+    bit-identical and agrees with the NCCL all-reduce path.
+"""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_rays
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from neuralvolumetricreconstructionformedicalimages_b200 import _lib
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder import get_encoder
+    from neuralvolumetricreconstructionformedicalimages_b200.engine import NAFEngine
+    from neuralvolumetricreconstructionformedicalimages_b200.network import get_network
+
+DEV = "cuda"
+
+
+def test_exchange_kernel_world1_bit_exact_vs_adam():
+    L_ = _lib.lib()
+    n = 4 * 25_003          # not a multiple of the block size
+    g = torch.Generator(device=DEV).manual_seed(5)
+    buf = _lib.peer_alloc(256 + 3 * n * 4)
+    flags = buf.tensor(0, _lib.XFLAG_WORDS, torch.int32, DEV)
+    param = buf.tensor(256, n, torch.float32, DEV)
+    grad0 = buf.tensor(256 + n * 4, n, torch.float32, DEV)
+    grad1 = buf.tensor(256 + 2 * n * 4, n, torch.float32, DEV)
+    param.copy_(torch.randn(n, device=DEV, generator=g))
+    grad0.copy_(torch.randn(n, device=DEV, generator=g) * 1e-2)
+    grad1.fill_(7.0)                                        # stale other-parity buffer: must come back zeroed
+    m = torch.randn(n, device=DEV, generator=g) * 1e-3
+    v = torch.rand(n, device=DEV, generator=g) * 1e-4
+    ref = [param.clone(), grad0.clone(), m.clone(), v.clone()]
+    x = _lib.Exchange()
+    x.world, x.rank, x.n = 1, 0, n
+    x.flags[0], x.param[0], x.grad[0] = buf.ptr, buf.ptr + 256, buf.ptr + 256 + n * 4
+    x.grad_zero = buf.ptr + 256 + 2 * n * 4
+    x.exp_avg, x.exp_avg_sq = m.data_ptr(), v.data_ptr()
+    for step in (1, 2, 9):
+        _lib.check(L_.nafb_adam_exchange_step(ctypes.byref(x), 1e-3, 0.9, 0.999, 1e-8, step, 1.0, _lib.stream_ptr()))
+        _lib.check(L_.nafb_adam_step(_lib.ptr(ref[0]), _lib.ptr(ref[1]), _lib.ptr(ref[2]), _lib.ptr(ref[3]), n, 1e-3, 0.9, 0.999, 1e-8, step,
+                                     1.0, 0, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(param, ref[0]) and torch.equal(m, ref[2]) and torch.equal(v, ref[3])
+        assert torch.equal(grad0, ref[1])                   # this step's gradient is left alone (its owner clears it next step)
+        assert int(grad1.abs().max().item()) == 0
+        f = flags.cpu().numpy()
+        assert f[_lib.XFLAG_ARRIVE] == step and f[_lib.XFLAG_DONE] == step and f[_lib.XFLAG_ERROR] == 0 and f[_lib.XFLAG_TICKET] == 0
+    i0, i1 = _lib.exchange_slice(n, 0, 1)
+    assert (i0, i1) == (0, n)
+    spans = [_lib.exchange_slice(n, r, 8) for r in range(8)]
+    assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] and a[0] % 4 == 0 for a, b in zip(spans, spans[1:]))
+    with pytest.raises(RuntimeError):
+        _lib.check(L_.nafb_adam_exchange_step(ctypes.byref(x), 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, _lib.stream_ptr()))
+    del flags, param, grad0, grad1
+    buf.release()
+
+
+def _net(dev, seed=0):
+    torch.manual_seed(seed)
+    enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
+    net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(dev)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-0.05, 0.05)
+    return net
+
+
+def _batches(rank, k, N=256, S=64):
+    rng = np.random.default_rng(10 + rank)
+    out = []
+    for _ in range(k):
+        rays = torch.from_numpy(make_rays(N, rng))
+        projs = torch.from_numpy(rng.uniform(0, 0.05, N).astype(np.float32))
+        t_rand = torch.from_numpy(rng.uniform(0, 1, (N, S)).astype(np.float32))
+        out.append((rays, projs, t_rand))
+    return out, S
+
+
+def test_engine_peer_mode_single_gpu_matches_default():
+    dev = torch.device("cuda", 0)
+    batches, S = _batches(0, 4)
+    params = []
+    for mode in ("peer", "auto"):
+        eng = NAFEngine(_net(dev), lr=1e-3, n_samples=S, perturb=True, loss_chunk=100, use_cuda_graph=(mode == "peer"), exchange=mode)
+        assert eng.exchange_mode == ("peer" if mode == "peer" else "local")
+        for rays, projs, t_rand in batches:
+            loss = eng.train_step(rays.to(dev), projs.to(dev), None, t_rand.to(dev))
+        torch.cuda.synchronize()
+        if eng.px is not None:
+            assert eng.px.error_word() == 0
+        sd = eng.optimizer_state_dict()
+        assert sd["exp_avg"].numel() == eng.n_params and sd["step"] == 4
+        params.append((eng.flat_param.clone(), sd["exp_avg_sq"], float(loss.item())))
+    (pa, va, la), (pb, vb, lb) = params
+    assert abs(la - lb) <= 1e-5 * abs(lb)
+    np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), rtol=0, atol=2e-5)     # 4 steps of lr 1e-3; float atomics order differs
+    np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=1e-3, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------- two ranks
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from neuralvolumetricreconstructionformedicalimages_b200 import parallel
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        batches, S = _batches(rank, 5)
+        res = {}
+        for mode in ("peer", "nccl"):
+            eng = NAFEngine(_net(dev, seed=rank), lr=1e-3, n_samples=S, perturb=True, loss_chunk=100, use_cuda_graph=True, exchange=mode)
+            assert eng.exchange_mode == mode, eng.exchange_mode
+            for rays, projs, t_rand in batches:
+                eng.train_step(rays.to(dev), projs.to(dev), None, t_rand.to(dev))
+            torch.cuda.synchronize()
+            div = parallel.replica_divergence(eng.flat_param)
+            err = eng.px.error_word() if eng.px is not None else 0
+            sd = eng.optimizer_state_dict()
+            res[mode] = dict(param=eng.flat_param.cpu(), v=sd["exp_avg_sq"].cpu(), div=div, err=err)
+        if rank == 0:
+            torch.save(res, os.path.join(out_dir, "res.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_peer_exchange_matches_nccl(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = torch.load(os.path.join(str(tmp_path), "res.pt"))
+    assert res["peer"]["err"] == 0
+    assert res["peer"]["div"] == 0.0 and res["nccl"]["div"] == 0.0       # replicas bit-identical
+    np.testing.assert_allclose(res["peer"]["param"].numpy(), res["nccl"]["param"].numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(res["peer"]["v"].numpy(), res["nccl"]["v"].numpy(), rtol=2e-3, atol=1e-12)
