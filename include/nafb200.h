@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 3
+#define NAFB_ABI_VERSION 4
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -103,13 +103,24 @@ enum nafb_point_source {
     NAFB_SRC_VOXELS = 2  /* voxel lattice of tigre.py:388-400, P = (i1-i0)*n2*n3       */
 };
 
+/* Device-resident state of the fused training step (8 x uint32): everything that changes from step to step, so that a
+ * captured CUDA graph of the whole iteration can be replayed without touching kernel arguments. */
+#define NAFB_STATE_STEP 0     /* completed optimizer steps (incremented by nafb_adam_step_dev / nafb_adam_exchange_step) */
+#define NAFB_STATE_SEED_LO 1  /* seed of the in-kernel sampler generator */
+#define NAFB_STATE_SEED_HI 2
+#define NAFB_STATE_LR 3       /* learning rate (float bits) */
+#define NAFB_STATE_TICKET 4   /* internal (zero between launches) */
+#define NAFB_STATE_WORDS 8
+
 typedef struct nafb_sampler {
     /* NAFB_SRC_POINTS */
     const float *pts;        /* [P,3] */
     uint64_t n_points;       /* P */
     /* NAFB_SRC_RAYS: reference src/render/render.py:88-105 */
     const float *rays;       /* [N,8] = origin(3), direction(3), near, far */
-    const float *t_rand;     /* [N,S] uniforms in [0,1) (torch.rand of render.py:99) or NULL when !perturb */
+    const float *t_rand;     /* [N,S] uniforms in [0,1) (torch.rand of render.py:99); NULL when !perturb or with rng_state */
+    const uint32_t *rng_state; /* device nafb_step_state: with perturb and t_rand == NULL the uniforms are generated
+                                  in-kernel from (seed, step, ray, sample) -- identical in forward and backward */
     uint32_t n_rays;
     uint32_t n_samples;
     int32_t perturb;
@@ -208,6 +219,9 @@ typedef struct nafb_exchange {
     float *grad_zero;                  /* local gradient buffer of the other parity, or NULL                    */
     float *exp_avg, *exp_avg_sq;       /* LOCAL, slice-sized: [i1 - i0] of nafb_exchange_slice(n, rank, world)  */
     uint64_t n;                        /* floats, multiple of 4                                                 */
+    uint32_t *state;                   /* optional device nafb_step_state: when non-NULL the epoch is state[0] + 1 and
+                                          the learning rate state[3] (the `step` / `lr` arguments are ignored), and
+                                          the kernel increments state[0]: the launch can sit in a replayed CUDA graph */
 } nafb_exchange;
 
 int nafb_peer_alloc(uint64_t bytes, void **ptr, unsigned char *handle64);
@@ -218,6 +232,12 @@ int nafb_peer_free(void *ptr);
 int nafb_exchange_slice(uint64_t n, uint32_t rank, uint32_t world, uint64_t *i0, uint64_t *i1);
 int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float beta2, float eps, uint32_t step,
                             float grad_scale, nafb_stream_t stream);
+
+/* Same optimizer step with the step count and learning rate taken from a device nafb_step_state: (the bias corrections
+ * are evaluated on the device in double precision, as torch does on the host); state[0] is incremented when the last
+ * block retires.  Graph-capturable: no argument changes from step to step. */
+int nafb_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float beta1, float beta2,
+                       float eps, float grad_scale, int zero_grad, uint32_t *state, nafb_stream_t stream);
 
 /* Arithmetic of the fused density kernels: 0 (default) = tcgen05 tensor cores with bf16x3 split
  * operands and fp32 TMEM accumulation wherever the configuration allows (4 x 32 MLP, skip at 2),

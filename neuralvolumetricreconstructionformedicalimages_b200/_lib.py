@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnafb200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NAFB_MAX_LEVELS = 32
 NAFB_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
@@ -43,6 +43,7 @@ class MlpGrads(ctypes.Structure):
 
 class Sampler(ctypes.Structure):
     _fields_ = [("pts", ctypes.c_void_p), ("n_points", u64), ("rays", ctypes.c_void_p), ("t_rand", ctypes.c_void_p),
+                ("rng_state", ctypes.c_void_p),
                 ("n_rays", u32), ("n_samples", u32), ("perturb", i32),
                 ("n1", u32), ("n2", u32), ("n3", u32), ("i0", u32), ("i1", u32),
                 ("s1", ctypes.c_double), ("s2", ctypes.c_double), ("s3", ctypes.c_double),
@@ -50,13 +51,14 @@ class Sampler(ctypes.Structure):
 
 
 NAFB_MAX_RANKS = 8
+STATE_STEP, STATE_SEED_LO, STATE_SEED_HI, STATE_LR, STATE_TICKET, STATE_WORDS = 0, 1, 2, 3, 4, 8
 XFLAG_ARRIVE, XFLAG_DONE, XFLAG_ERROR, XFLAG_TICKET, XFLAG_WORDS = 0, 8, 16, 17, 32
 
 
 class Exchange(ctypes.Structure):
     _fields_ = [("world", u32), ("rank", u32), ("param", ctypes.c_void_p * NAFB_MAX_RANKS), ("grad", ctypes.c_void_p * NAFB_MAX_RANKS),
                 ("flags", ctypes.c_void_p * NAFB_MAX_RANKS), ("grad_zero", ctypes.c_void_p), ("exp_avg", ctypes.c_void_p),
-                ("exp_avg_sq", ctypes.c_void_p), ("n", u64)]
+                ("exp_avg_sq", ctypes.c_void_p), ("n", u64), ("state", ctypes.c_void_p)]
 
 
 _SIGNATURES = {
@@ -84,6 +86,8 @@ _SIGNATURES = {
     "nafb_set_mlp_mode": (ctypes.c_int, [ctypes.c_int]),
     "nafb_microbench": (ctypes.c_int, [ctypes.c_int, c_f32p, u32, ctypes.c_int, c_f32p, ctypes.POINTER(u64), ctypes.c_void_p]),
     "nafb_selftest_umma": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_void_p]),
+    "nafb_adam_step_dev": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "nafb_adam_step": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, u32, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
 }
 

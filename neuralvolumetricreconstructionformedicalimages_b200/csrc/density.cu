@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(TILE, 3) k_density_fwd(const GridParams gp, co
                     contrib = __fmul_rn(y, ray_delta(sp, R, r, i));   // render.py:201
                     if (z_out)
                         z_out[p] = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
-                                            sp.t_rand ? sp.t_rand + (size_t)r * sp.n_samples : nullptr);
+                                            jitter_for(sp, r));
                 }
                 if (acc_out) {
                     // warp-shuffle segmented reduction over the ray id, one atomic per (warp, ray) segment

@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, c
                         contrib = __fmul_rn(y, ray_delta(sp, R, ray, i));  // render.py:201
                         if (z_out)
                             z_out[p] = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
-                                                sp.t_rand ? sp.t_rand + (size_t)ray * sp.n_samples : nullptr);
+                                                jitter_for(sp, ray));
                     }
                     if (acc_out) {  // warp-shuffle segmented reduction keyed by the ray id
 #pragma unroll

@@ -24,25 +24,12 @@
 #include <math.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "adam.cuh"
 
 namespace {
 
 constexpr int MAXR = NAFB_MAX_RANKS;
 constexpr unsigned long long TIMEOUT_NS = 4000000000ull;   // 4 s
-
-struct AdamConst {
-    float w1, beta2, w2, bc2_sqrt, eps, neg_step, gscale;
-};
-
-__device__ __forceinline__ void adam_one(float &p, const float g, float &m, float &v, const AdamConst &c) {
-    const float gg = __fmul_rn(g, c.gscale);
-    m = __fmaf_rn(c.w1, __fsub_rn(gg, m), m);
-    v = __fmul_rn(v, c.beta2);
-    v = __fmaf_rn(__fmul_rn(c.w2, gg), gg, v);
-    const float dn = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
-    p = __fmaf_rn(c.neg_step, __fdiv_rn(m, dn), p);
-}
 
 struct ExchangeParams {
     uint32_t world, rank, epoch;
@@ -52,7 +39,9 @@ struct ExchangeParams {
     float *grad_zero;
     float *m, *v;          // slice-local
     uint64_t n4, s0, s1;   // float4 units
-    AdamConst c;
+    AdamConst c;           // host-evaluated constants (state == nullptr)
+    uint32_t *state;       // device step state, or nullptr
+    float beta1, beta2, eps, gscale;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -73,11 +62,11 @@ __device__ __forceinline__ float4 ld_peer(const float4 *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_peer(float4 *p, const float4 v) { __stcg(p, v); }
 
 // wait until flag word `idx0 + w` of the LOCAL block is >= epoch for every rank w
-__device__ __forceinline__ void wait_all(const ExchangeParams &P, uint32_t idx0) {
+__device__ __forceinline__ void wait_all(const ExchangeParams &P, uint32_t idx0, uint32_t epoch) {
     if (threadIdx.x < P.world) {
         const uint32_t *f = P.flags[P.rank] + idx0 + threadIdx.x;
         const unsigned long long t0 = globaltimer_ns();
-        while ((int32_t)(ld_acquire_sys(f) - P.epoch) < 0) {
+        while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
             if (globaltimer_ns() - t0 > TIMEOUT_NS) {
                 atomicExch(P.flags[P.rank] + NAFB_XFLAG_ERROR, 1u + idx0 + threadIdx.x);
                 break;
@@ -91,12 +80,21 @@ __device__ __forceinline__ void wait_all(const ExchangeParams &P, uint32_t idx0)
 template <int W>
 __global__ void __launch_bounds__(512) k_adam_exchange(const ExchangeParams P) {
     const uint32_t world = W > 0 ? (uint32_t)W : P.world;
+    __shared__ AdamConst s_c;
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = P.state ? P.state[NAFB_STATE_STEP] + 1u : P.epoch;
+        s_c = P.state ? adam_const_from_state(P.state, P.beta1, P.beta2, P.eps, P.gscale) : P.c;
+    }
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    const AdamConst c = s_c;
     // ---- 1. tell every rank (myself included) that my gradient is complete, then wait for everybody's
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
-        st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_ARRIVE + P.rank, P.epoch);
+        st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_ARRIVE + P.rank, epoch);
     }
-    wait_all(P, NAFB_XFLAG_ARRIVE);
+    wait_all(P, NAFB_XFLAG_ARRIVE, epoch);
 
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     // ---- 2. clear my gradient buffer of the other parity (its readers finished before they arrived at this epoch)
@@ -129,10 +127,10 @@ __global__ void __launch_bounds__(512) k_adam_exchange(const ExchangeParams P) {
 #pragma unroll
                 for (int w = 1; w < MAXR; ++w)
                     if (w < (int)world) { s.x += g[u][w].x; s.y += g[u][w].y; s.z += g[u][w].z; s.w += g[u][w].w; }
-                adam_one(p[u].x, s.x, m[u].x, v[u].x, P.c);
-                adam_one(p[u].y, s.y, m[u].y, v[u].y, P.c);
-                adam_one(p[u].z, s.z, m[u].z, v[u].z, P.c);
-                adam_one(p[u].w, s.w, m[u].w, v[u].w, P.c);
+                adam_one(p[u].x, s.x, m[u].x, v[u].x, c);
+                adam_one(p[u].y, s.y, m[u].y, v[u].y, c);
+                adam_one(p[u].z, s.z, m[u].z, v[u].z, c);
+                adam_one(p[u].w, s.w, m[u].w, v[u].w, c);
                 m4[i - P.s0] = m[u];
                 v4[i - P.s0] = v[u];
 #pragma unroll
@@ -150,8 +148,9 @@ __global__ void __launch_bounds__(512) k_adam_exchange(const ExchangeParams P) {
     if (!s_last) return;
     __threadfence_system();
     if (threadIdx.x == 0) P.flags[P.rank][NAFB_XFLAG_TICKET] = 0u;
-    if (threadIdx.x < world) st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_DONE + P.rank, P.epoch);
-    wait_all(P, NAFB_XFLAG_DONE);
+    if (threadIdx.x < world) st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_DONE + P.rank, epoch);
+    wait_all(P, NAFB_XFLAG_DONE, epoch);
+    if (P.state && threadIdx.x == 0) P.state[NAFB_STATE_STEP] = epoch;   // every block has read the old value long ago
 }
 
 }  // namespace
@@ -212,7 +211,7 @@ int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float
                             nafb_stream_t stream) {
     if (!x) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: null descriptor");
     if (x->world < 1 || x->world > NAFB_MAX_RANKS || x->rank >= x->world) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: world %u / rank %u", x->world, x->rank);
-    if (step == 0) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: step is 1-based");
+    if (step == 0 && !x->state) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: step is 1-based");
     if (x->n == 0 || (x->n & 3)) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: n must be a positive multiple of 4");
     if (!x->exp_avg || !x->exp_avg_sq) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: null optimizer state");
     ExchangeParams P{};
@@ -229,10 +228,8 @@ int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float
     int rc = nafb_exchange_slice(x->n, x->rank, x->world, &i0, &i1);
     if (rc) return rc;
     P.n4 = x->n >> 2; P.s0 = i0 >> 2; P.s1 = i1 >> 2;
-    const double b1 = (double)beta1, b2 = (double)beta2;
-    const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
-    P.c.w1 = (float)(1.0 - b1); P.c.beta2 = beta2; P.c.w2 = (float)(1.0 - b2); P.c.bc2_sqrt = (float)sqrt(bc2); P.c.eps = eps;
-    P.c.neg_step = (float)(-((double)lr / bc1)); P.c.gscale = grad_scale;
+    P.c = make_adam_const((double)lr, beta1, beta2, eps, step ? step : 1u, grad_scale);
+    P.state = x->state; P.beta1 = beta1; P.beta2 = beta2; P.eps = eps; P.gscale = grad_scale;
     // persistent grid: as many blocks of 512 threads as are resident at once (blocks spin on the arrival flags)
     cudaStream_t s = (cudaStream_t)stream;
     auto launch = [&](auto kernel) {

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(128) k_sample_points(const SamplerParams sp, f
     const uint32_t r = blockIdx.x;
     const uint32_t S = sp.n_samples;
     const RayRegs R = load_ray(sp.rays, r);
-    const float *tr = sp.t_rand ? sp.t_rand + (size_t)r * S : nullptr;
+    const Jitter tr = jitter_for(sp, r);
     float tv = 0.f;
     for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
         const float z = z_sample(R.near, R.far, i, S, sp.lin_step, sp.perturb != 0, tr);

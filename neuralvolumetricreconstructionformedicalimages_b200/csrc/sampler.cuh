@@ -12,6 +12,7 @@ struct SamplerParams {
     const float *pts;
     const float *rays;
     const float *t_rand;
+    const uint32_t *rng_state;   // device nafb_step_state (step, seed): in-kernel uniforms when t_rand is NULL
     uint32_t n_rays, n_samples;
     int32_t perturb;
     uint32_t n1, n2, n3, i0, i1;
@@ -34,15 +35,36 @@ __device__ __forceinline__ float z_uniform(float near, float far, uint32_t i, ui
     return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
 }
 
+// Where the uniforms of render.py:99 (torch.rand([n_rays, n_samples])) come from: a tensor the caller filled
+// (bit-exact parity with a given draw), or a counter-based generator evaluated in-kernel -- same value for the same
+// (seed, step, ray, sample) in the forward and the backward kernel, no [N,S] buffer, no generator launch.
+// splitmix64 of the 64-bit counter, top 24 bits -> multiples of 2^-24 in [0,1) like torch.rand for float32.
+struct Jitter {
+    const float *row;   // t_rand + ray * S, or nullptr
+    uint64_t key;       // generator key of this step (seed and step folded together)
+    uint64_t base;      // ray * S
+};
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ float jitter_uniform(const Jitter &j, uint32_t i) {
+    if (j.row) return __ldg(j.row + i);
+    const uint64_t z = splitmix64(j.key + (j.base + i) * 0x9E3779B97F4A7C15ull);
+    return (float)(uint32_t)(z >> 40) * 5.9604644775390625e-08f;   // 2^-24
+}
+
 // perturbed sample i of a ray (render.py:95-100): lower + (upper-lower)*t_rand
-__device__ __forceinline__ float z_sample(float near, float far, uint32_t i, uint32_t S, float step, bool perturb,
-                                          const float *__restrict__ t_rand_row) {
+__device__ __forceinline__ float z_sample(float near, float far, uint32_t i, uint32_t S, float step, bool perturb, const Jitter &jit) {
     const float zi = z_uniform(near, far, i, S, step);
     if (!perturb) return zi;
     float lower = zi, upper = zi;
     if (i > 0) lower = __fmul_rn(0.5f, __fadd_rn(zi, z_uniform(near, far, i - 1, S, step)));
     if (i + 1 < S) upper = __fmul_rn(0.5f, __fadd_rn(z_uniform(near, far, i + 1, S, step), zi));
-    return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(t_rand_row + i)));
+    return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), jitter_uniform(jit, i)));
 }
 
 struct RayRegs {
@@ -73,6 +95,18 @@ __device__ __forceinline__ float voxel_coord(uint32_t i, uint32_t n, double s) {
     return (float)__dadd_rn(__dmul_rn((double)i, step), -s);
 }
 
+__device__ __forceinline__ Jitter jitter_for(const SamplerParams &sp, uint32_t ray) {
+    Jitter j;
+    j.row = sp.t_rand ? sp.t_rand + (size_t)ray * sp.n_samples : nullptr;
+    j.base = (uint64_t)ray * sp.n_samples;
+    j.key = 0;
+    if (!sp.t_rand && sp.rng_state && sp.perturb) {
+        const uint64_t seed = (uint64_t)__ldg(sp.rng_state + 1) | ((uint64_t)__ldg(sp.rng_state + 2) << 32);
+        j.key = splitmix64(seed + (uint64_t)__ldg(sp.rng_state) * 0xD1342543DE82EF95ull);
+    }
+    return j;
+}
+
 // Fetch point p of the launch (world coordinates). For RAYS also yields ray/sample index.
 template <int SRC>
 __device__ __forceinline__ void fetch_point(const SamplerParams &sp, uint64_t p, float (&x)[3]) {
@@ -83,8 +117,7 @@ __device__ __forceinline__ void fetch_point(const SamplerParams &sp, uint64_t p,
     } else if constexpr (SRC == NAFB_SRC_RAYS) {
         const uint32_t r = (uint32_t)(p / sp.n_samples), i = (uint32_t)(p - (uint64_t)r * sp.n_samples);
         const RayRegs R = load_ray(sp.rays, r);
-        const float z = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
-                                 sp.t_rand ? sp.t_rand + (size_t)r * sp.n_samples : nullptr);
+        const float z = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0, jitter_for(sp, r));
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[d] = ray_point(R.o[d], R.d[d], z, sp.clamp);
     } else {
@@ -101,7 +134,7 @@ __device__ __forceinline__ void fetch_point(const SamplerParams &sp, uint64_t p,
 // delta_i * |d| of raw2outputs (render.py:192-194): (z[i+1]-z[i]) * norm, last = 1e-10 * norm
 __device__ __forceinline__ float ray_delta(const SamplerParams &sp, const RayRegs &R, uint32_t r, uint32_t i) {
     const uint32_t S = sp.n_samples;
-    const float *tr = sp.t_rand ? sp.t_rand + (size_t)r * S : nullptr;
+    const Jitter tr = jitter_for(sp, r);
     float dist;
     if (i + 1 < S) {
         const float z0 = z_sample(R.near, R.far, i, S, sp.lin_step, sp.perturb != 0, tr);
@@ -125,7 +158,7 @@ __device__ __forceinline__ float normalise01(float x, float bound, float inv_2bo
 static inline int nafb_make_sampler_params(const nafb_sampler *s, int src, SamplerParams *out, uint64_t *n_points) {
     if (!s) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: null");
     SamplerParams p{};
-    p.pts = s->pts; p.rays = s->rays; p.t_rand = s->t_rand;
+    p.pts = s->pts; p.rays = s->rays; p.t_rand = s->t_rand; p.rng_state = s->rng_state;
     p.n_rays = s->n_rays; p.n_samples = s->n_samples; p.perturb = s->perturb;
     p.n1 = s->n1; p.n2 = s->n2; p.n3 = s->n3; p.i0 = s->i0; p.i1 = s->i1;
     p.s1 = s->s1; p.s2 = s->s2; p.s3 = s->s3;
@@ -142,7 +175,8 @@ static inline int nafb_make_sampler_params(const nafb_sampler *s, int src, Sampl
         case NAFB_SRC_RAYS:
             n = (uint64_t)s->n_rays * s->n_samples;
             if (n && !s->rays) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: rays is null");
-            if (n && s->perturb && !s->t_rand) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: perturb needs t_rand");
+            if (n && s->perturb && !s->t_rand && !s->rng_state)
+                NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: perturb needs t_rand (or rng_state for in-kernel uniforms)");
             break;
         case NAFB_SRC_VOXELS:
             if (s->i1 > s->n1 || s->i0 > s->i1) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: bad voxel slab");

@@ -133,7 +133,7 @@ class PeerExchange:
 
 class NAFEngine:
     def __init__(self, net: DensityNetwork, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, n_samples=192, perturb=True, loss_chunk=None,
-                 use_cuda_graph=True, process_group=None, use_stash=True, exchange="auto"):
+                 use_cuda_graph=True, process_group=None, use_stash=True, exchange="auto", seed=None):
         meta = net.fused_meta()
         if meta is None:
             raise RuntimeError("NAFEngine needs a DensityNetwork in a fused-capable configuration "
@@ -143,7 +143,8 @@ class NAFEngine:
             raise RuntimeError("NAFEngine needs the network on a CUDA device (there is no CPU path)")
         _lib.lib()
         self.net, self.meta, self.device = net, meta, dev
-        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.state = None
+        self._lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.n_samples, self.perturb, self.loss_chunk = int(n_samples), bool(perturb), loss_chunk
         self.step_count = 0
         self.use_cuda_graph = use_cuda_graph
@@ -156,7 +157,9 @@ class NAFEngine:
         self._flatten(exchange)
         if self.world_size > 1:   # replicas start identical
             parallel.broadcast_(self.flat_param, 0, process_group)
+        self._init_state(seed)
         self._graphs = {}
+        self._eager_runs = {}
         self._static = {}
 
     # ------------------------------------------------------------------ flat parameter vector
@@ -225,15 +228,47 @@ class NAFEngine:
         """Which gradient buffer the coming step accumulates into (peer exchange: alternates; otherwise always 0)."""
         return (self.step_count & 1) if self.px is not None else 0
 
+    # ------------------------------------------------------------------ device-resident step state
+    def _init_state(self, seed):
+        """nafb_step_state: [step, seed_lo, seed_hi, lr bits, ticket, ...] -- what changes from step to step lives on the
+        device, so one captured graph replays the whole iteration (sampler uniforms and Adam's bias corrections included)."""
+        seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        seed ^= (0x9E3779B97F4A7C15 * (self.rank + 1)) & 0xFFFFFFFFFFFFFFFF      # every rank draws its own jitter
+        st = np.zeros(_lib.STATE_WORDS, dtype=np.uint32)
+        st[_lib.STATE_SEED_LO], st[_lib.STATE_SEED_HI] = seed & 0xFFFFFFFF, seed >> 32
+        st[_lib.STATE_LR] = np.float32(self._lr).view(np.uint32)
+        self.state = torch.from_numpy(st.view(np.int32)).to(self.device)
+        if self.px is not None:
+            for x in self.px.desc:
+                x.state = self.state.data_ptr()
+
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        """Learning rate (follow a scheduler by assignment); mirrored into the device state the kernels read."""
+        self._lr = float(value)
+        if getattr(self, "state", None) is not None:
+            self.state[_lib.STATE_LR : _lib.STATE_LR + 1] = torch.tensor([np.float32(self._lr).view(np.int32)], dtype=torch.int32)
+
+    def _set_step(self, step):
+        self.step_count = int(step)
+        self.state[_lib.STATE_STEP : _lib.STATE_STEP + 1] = torch.tensor([self.step_count], dtype=torch.int32)
+
     # ------------------------------------------------------------------ one training step
     def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None, stash=None, par=0):
+        """density_fwd -> mse_loss -> density_bwd (+ reduce).  t_rand None: the sampler draws its uniforms in-kernel."""
         L_ = _lib.lib()
         tm = timer or _NoTimer()
         N = rays.shape[0]
         # acc is zero on entry: allocated zeroed, and mse_loss clears it after reading (zero_pred)
         grid = self.meta.grid(self.table)
         mlp = self.meta.mlp(self.mlp_params)
-        smp = self.meta.sampler(rays=rays.data_ptr(), t_rand=t_rand.data_ptr() if self.perturb else None, n_rays=N,
+        explicit = self.perturb and t_rand is not None
+        smp = self.meta.sampler(rays=rays.data_ptr(), t_rand=t_rand.data_ptr() if explicit else None,
+                                rng_state=self.state.data_ptr() if (self.perturb and not explicit) else None, n_rays=N,
                                 n_samples=self.n_samples, perturb=int(self.perturb))
         st = _lib.stream_ptr()
         with tm("density_fwd"):
@@ -244,47 +279,60 @@ class NAFEngine:
             _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), 1, st))
         with tm("density_bwd"):
             gv = self._grad_views[par]
-            density_backward(self.meta, self.table, self.mlp_params, dacc, gv[0], gv[1:], rays=rays, t_rand=t_rand,
-                             n_samples=self.n_samples, perturb=self.perturb, stash=stash)
+            density_backward(self.meta, self.table, self.mlp_params, dacc, gv[0], gv[1:], rays=rays, t_rand=t_rand if explicit else None,
+                             n_samples=self.n_samples, perturb=self.perturb, stash=stash, rng_state=None if explicit else self.state)
 
-    def _exchange_and_adam(self, par, timer=None):
-        """The step's exchange + optimizer: peer kernel, or (NCCL all-reduce +) the dense Adam kernel."""
+    def _optimizer_kernel(self, par, timer=None):
+        """Peer mode: the fused exchange kernel.  Otherwise the dense Adam kernel.  Both take step / lr from the device state
+        and increment the step when their last block retires (graph-capturable)."""
         L_ = _lib.lib()
         tm = timer or _NoTimer()
-        self.step_count += 1
         if self.px is not None:
             with tm("adam_exchange"):
-                self.px.step(par, self.lr, self.betas, self.eps, self.step_count, _lib.stream_ptr())
+                self.px.step(par, self._lr, self.betas, self.eps, 0, _lib.stream_ptr())
             return
-        if self.world_size > 1:
-            with tm("all_reduce"):
-                parallel.allreduce_sum_(self.flat_grad, self.pg)
         with tm("adam"):
-            _lib.check(L_.nafb_adam_step(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
-                                         _lib.ptr(self.exp_avg_sq), self.n_params, self.lr, self.betas[0], self.betas[1], self.eps,
-                                         self.step_count, 1.0 / self.world_size, 1, _lib.stream_ptr()))
+            _lib.check(L_.nafb_adam_step_dev(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                             _lib.ptr(self.exp_avg_sq), self.n_params, self.betas[0], self.betas[1], self.eps,
+                                             1.0 / self.world_size, 1, _lib.ptr(self.state), _lib.stream_ptr()))
 
-    # kernels of this library launched by one train_step (density_fwd, mse_loss, density_bwd, reduce_partials, adam)
+    def _whole_step(self, s, par, timer=None, t_rand=None, with_optimizer=True):
+        self._step_kernels(s["rays"], s["projs"], s["mask"], t_rand, s["loss"], s["dacc"], s["acc"], timer, stash=s["stash"], par=par)
+        if with_optimizer:
+            self._finish_step(par, timer)
+
+    def _finish_step(self, par, timer=None):
+        if self.world_size > 1 and self.px is None:
+            with (timer or _NoTimer())("all_reduce"):
+                parallel.allreduce_sum_(self.flat_grad, self.pg)
+        self._optimizer_kernel(par, timer)
+
+    # kernels of this library launched by one train_step (density_fwd, mse_loss, density_bwd, reduce_partials, adam / adam_exchange)
     LAUNCHES_PER_STEP = 5
+
+    def _load_inputs(self, s, rays, projs, mask, t_rand):
+        """Inputs -> the static buffers the graph reads (device tensors, or pinned host tensors: one H2D copy each)."""
+        N = s["rays"].shape[0]
+        s["rays"].copy_(rays.reshape(N, 8), non_blocking=True)
+        s["projs"].copy_(projs.reshape(N), non_blocking=True)
+        if mask is not None:
+            s["mask"].copy_(mask.reshape(N), non_blocking=True)
+        if self.perturb and t_rand is not None:
+            if s["t_rand"] is None:
+                s["t_rand"] = torch.zeros(N, self.n_samples, device=self.device)
+            s["t_rand"].copy_(t_rand, non_blocking=True)
+            return s["t_rand"]
+        return None
 
     def profiled_step(self, rays, projs, mask, t_rand, timer):
         """Same work as train_step, launched eagerly (no graph) with a CUDA-event pair around every kernel."""
         N = rays.shape[0]
         s = self._get_static(N, mask is not None)
         with torch.cuda.device(self.device):
-            s["rays"].copy_(rays.reshape(N, 8))
-            s["projs"].copy_(projs.reshape(N))
-            if mask is not None:
-                s["mask"].copy_(mask.reshape(N))
-            if self.perturb:
-                with timer("t_rand"):
-                    if t_rand is None:
-                        s["t_rand"].uniform_(0.0, 1.0)
-                    else:
-                        s["t_rand"].copy_(t_rand)
+            tr = self._load_inputs(s, rays, projs, mask, t_rand)
             par = self._parity()
-            self._step_kernels(s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"], timer, stash=s["stash"], par=par)
-            self._exchange_and_adam(par, timer)
+            self._whole_step(s, par, timer, tr)
+            self.step_count += 1
         return s["loss"][0]
 
     def _get_static(self, N, with_mask):
@@ -295,52 +343,42 @@ class NAFEngine:
             nb = stash_bytes(self.meta, self.table, self.mlp_params, N * self.n_samples) if self.use_stash else 0
             s = dict(rays=torch.zeros(N, 8, device=d), projs=torch.zeros(N, device=d),
                      stash=torch.empty(nb, dtype=torch.uint8, device=d) if nb else None,
-                     mask=torch.ones(N, device=d, dtype=torch.uint8) if with_mask else None,
-                     t_rand=torch.zeros(N, self.n_samples, device=d) if self.perturb else None,
+                     mask=torch.ones(N, device=d, dtype=torch.uint8) if with_mask else None, t_rand=None,
                      loss=torch.zeros(2, device=d), dacc=torch.zeros(N, device=d), acc=torch.zeros(N, device=d))
             self._static[key] = s
         return s
 
     def train_step(self, rays, projs, mask=None, t_rand=None):
-        """rays [N,8], projs [N] (+ optional uint8/bool mask [N], uniforms t_rand [N,S]) on the device.
+        """One optimisation step.  rays [N,8], projs [N] (+ optional uint8/bool mask [N]) on the device or in pinned host
+        memory; t_rand [N,S]: explicit uniforms of render.py:99 (parity runs) -- by default the kernels draw them themselves.
         Returns the loss as a 0-dim device tensor (no host synchronisation)."""
         N = rays.shape[0]
         s = self._get_static(N, mask is not None)
         with torch.cuda.device(self.device):
-            s["rays"].copy_(rays.reshape(N, 8), non_blocking=True)
-            s["projs"].copy_(projs.reshape(N), non_blocking=True)
-            if mask is not None:
-                s["mask"].copy_(mask.reshape(N), non_blocking=True)
-            if self.perturb:
-                if t_rand is None:
-                    s["t_rand"].uniform_(0.0, 1.0)  # on-device Philox, same distribution as torch.rand (render.py:99)
-                else:
-                    s["t_rand"].copy_(t_rand, non_blocking=True)
+            tr = self._load_inputs(s, rays, projs, mask, t_rand)
             par = self._parity()
-            self._run_fwd_bwd(s, (N, mask is not None, par), par)
-            self._exchange_and_adam(par)
+            key = (N, mask is not None, par, tr is not None)
+            # one graph per (shape, parity) holds the whole iteration; only an NCCL all-reduce (+ the Adam after it) stays outside
+            in_graph = not (self.world_size > 1 and self.px is None)
+            if not self.use_cuda_graph:
+                self._whole_step(s, par, None, tr)
+            else:
+                g = self._graphs.get(key)
+                if g is None and self._eager_runs.get(key, 0) < 1:
+                    # first use of a shape: run eagerly (kernel attributes / lazy module loading must not happen under capture)
+                    self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
+                    self._whole_step(s, par, None, tr)
+                else:
+                    if g is None:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._whole_step(s, par, None, tr, with_optimizer=in_graph)
+                        self._graphs[key] = g   # capture does not execute: the replay below performs this step
+                    g.replay()
+                    if not in_graph:
+                        self._finish_step(par)
+            self.step_count += 1
         return s["loss"][0]
-
-    def _run_fwd_bwd(self, s, key, par):
-        args = (s["rays"], s["projs"], s["mask"], s["t_rand"], s["loss"], s["dacc"], s["acc"])
-        if not self.use_cuda_graph:
-            self._step_kernels(*args, stash=s["stash"], par=par)
-            return
-        g = self._graphs.get(key)
-        if g is None:
-            # warm up on a side stream (lazy kernel attribute setup must not happen under capture)
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self._step_kernels(*args, stash=s["stash"], par=par)
-                self.flat_grads[par].zero_()  # the gradient is zero between steps (the optimizer kernel clears it)
-            torch.cuda.current_stream().wait_stream(side)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_kernels(*args, stash=s["stash"], par=par)
-            self._graphs[key] = g
-            # capture does not execute: replay below performs the first real step
-        g.replay()
 
     # ------------------------------------------------------------------ inference
     @torch.no_grad()
@@ -386,14 +424,14 @@ class NAFEngine:
 
     def optimizer_state_dict(self):
         return {"step": self.step_count, "exp_avg": self._full_state(self.exp_avg), "exp_avg_sq": self._full_state(self.exp_avg_sq),
-                "lr": self.lr}
+                "lr": self._lr}
 
     def load_optimizer_state_dict(self, sd):
-        self.step_count = int(sd["step"])
+        self._set_step(sd["step"])
         i0, i1 = self.px.slice if self.px is not None else (0, self.n_params)
         self.exp_avg.copy_(sd["exp_avg"][i0:i1])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"][i0:i1])
-        self.lr = float(sd.get("lr", self.lr))
+        self.lr = float(sd.get("lr", self._lr))
         if self.px is not None:   # the parity of step_count selects the gradient buffer: both must be clean
             for g in self.flat_grads:
                 g.zero_()

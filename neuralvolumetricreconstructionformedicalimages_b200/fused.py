@@ -119,7 +119,7 @@ def density_forward(meta: NetMeta, table, params, *, pts=None, rays=None, t_rand
 
 
 def density_backward(meta: NetMeta, table, params, dsig_or_dacc, grad_table, grad_params, *, pts=None, rays=None, t_rand=None,
-                     n_samples=0, perturb=False, stash=None):
+                     n_samples=0, perturb=False, stash=None, rng_state=None):
     """Accumulates into grad_table / grad_params (list aligned with params; entries may be None).
     `stash` is what density_forward(want_stash=True) returned for the same points, or None."""
     L_ = _lib.lib()
@@ -132,6 +132,7 @@ def density_backward(meta: NetMeta, table, params, dsig_or_dacc, grad_table, gra
         src = _lib.SRC_POINTS
     else:
         smp = meta.sampler(rays=rays.data_ptr(), t_rand=t_rand.data_ptr() if (perturb and t_rand is not None) else None,
+                           rng_state=rng_state.data_ptr() if (perturb and t_rand is None and rng_state is not None) else None,
                            n_rays=rays.shape[0], n_samples=n_samples, perturb=int(bool(perturb)))
         src = _lib.SRC_RAYS
     ws = _workspace(mlp, dev)

@@ -477,6 +477,66 @@ def test_adam_matches_torch():
     print("adam bit-exact vs torch.optim.Adam:", exact)
 
 
+def test_adam_dev_state_and_kernel_rng():
+    """(a) nafb_adam_step_dev (step / lr read from the device state, bias corrections evaluated on the device) reproduces
+    nafb_adam_step and advances the step; (b) the in-kernel sampler uniforms: forward and backward see the same draw (the
+    fused step equals a step with the same uniforms fed explicitly is not observable, so we check determinism per
+    (seed, step), change with the step, and the statistics of the jitter through z_vals)."""
+    L_ = _lib.lib()
+    n = 4 * 10_001
+    g = torch.Generator(device=DEV).manual_seed(11)
+    p0 = torch.randn(n, device=DEV, generator=g)
+    g0 = torch.randn(n, device=DEV, generator=g) * 1e-2
+    a = [p0.clone(), g0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)]
+    b = [p0.clone(), g0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)]
+    state = torch.zeros(_lib.STATE_WORDS, dtype=torch.int32, device=DEV)
+    state[_lib.STATE_LR] = int(np.float32(2e-3).view(np.int32))
+    for step in range(1, 6):
+        _lib.check(L_.nafb_adam_step(_lib.ptr(a[0]), _lib.ptr(a[1]), _lib.ptr(a[2]), _lib.ptr(a[3]), n, 2e-3, 0.9, 0.999, 1e-8, step, 0.5, 0,
+                                     _lib.stream_ptr()))
+        _lib.check(L_.nafb_adam_step_dev(_lib.ptr(b[0]), _lib.ptr(b[1]), _lib.ptr(b[2]), _lib.ptr(b[3]), n, 0.9, 0.999, 1e-8, 0.5, 0,
+                                         _lib.ptr(state), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert int(state[_lib.STATE_STEP].item()) == step and int(state[_lib.STATE_TICKET].item()) == 0
+        for x, y in zip(a, b):
+            np.testing.assert_allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=1e-6, atol=0)
+    # ---- in-kernel uniforms, observed through z_vals of the fused forward
+    from neuralvolumetricreconstructionformedicalimages_b200.fused import density_forward
+    net = _chest_net()
+    meta = net.fused_meta()
+    table = net.encoder.embeddings.detach()
+    ps = [q.detach() for q in net.flat_params()]
+    rng = np.random.default_rng(2)
+    N, S = 64, 192
+    rays = torch.from_numpy(make_rays(N, rng)).to(DEV)
+
+    def z_of(step, seed):
+        st = torch.zeros(_lib.STATE_WORDS, dtype=torch.int32, device=DEV)
+        st[_lib.STATE_STEP], st[_lib.STATE_SEED_LO] = step, seed
+        grid, mlp = meta.grid(table), meta.mlp(ps)
+        smp = meta.sampler(rays=rays.data_ptr(), t_rand=None, rng_state=st.data_ptr(), n_rays=N, n_samples=S, perturb=1)
+        z = torch.empty(N, S, device=DEV)
+        acc = torch.zeros(N, device=DEV)
+        _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, None, _lib.ptr(acc),
+                                           _lib.ptr(z), None, None, None, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        return z.cpu().numpy()
+
+    z1, z1b, z2, z3 = z_of(1, 7), z_of(1, 7), z_of(2, 7), z_of(1, 8)
+    assert np.array_equal(z1, z1b) and not np.array_equal(z1, z2) and not np.array_equal(z1, z3)
+    # recover the uniforms: z = lower + (upper - lower) * u on the stratified bins of render.py:95-100
+    near, far = rays[:, 6:7].cpu().numpy(), rays[:, 7:8].cpu().numpy()
+    t = naf.linspace01(S)[None, :]
+    zu = near * (1 - t) + far * t
+    mids = 0.5 * (zu[:, 1:] + zu[:, :-1])
+    lower = np.concatenate([zu[:, :1], mids], 1)
+    upper = np.concatenate([mids, zu[:, -1:]], 1)
+    u = ((z1 - lower) / np.maximum(upper - lower, 1e-12))[:, 1:-1].astype(np.float64)
+    assert u.min() >= -1e-3 and u.max() <= 1 + 1e-3
+    assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005           # 12 160 draws: sigma(mean) = 0.0026
+    assert abs(np.corrcoef(u[:, :-1].ravel(), u[:, 1:].ravel())[0, 1]) < 0.03      # neighbouring samples are uncorrelated
+
+
 @both_modes
 def test_engine_train_steps_vs_oracle(mlp_mode):
     """Five fused steps (graph replay) track five oracle steps (CPU autograd + torch Adam)."""

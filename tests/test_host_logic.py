@@ -114,16 +114,16 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == _lib.exported_symbols()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.nafb_abi_version() == 3
+    assert L.nafb_abi_version() == 4
     # struct layouts agree with the C header (sizes computed by the C compiler)
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "nafb200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(nafb_grid), sizeof(nafb_mlp), sizeof(nafb_mlp_grads), sizeof(nafb_sampler));}'
+    src = '#include <stdio.h>\n#include "nafb200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(nafb_grid), sizeof(nafb_mlp), sizeof(nafb_mlp_grads), sizeof(nafb_sampler), sizeof(nafb_exchange));}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
-    assert sizes == [ctypes.sizeof(_lib.Grid), ctypes.sizeof(_lib.Mlp), ctypes.sizeof(_lib.MlpGrads), ctypes.sizeof(_lib.Sampler)]
+    assert sizes == [ctypes.sizeof(_lib.Grid), ctypes.sizeof(_lib.Mlp), ctypes.sizeof(_lib.MlpGrads), ctypes.sizeof(_lib.Sampler), ctypes.sizeof(_lib.Exchange)]
     # argument validation happens before any launch: safe to exercise without a GPU
     assert L.nafb_adam_step(None, None, None, None, 4, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, 1, None) == _lib.ERR_INVALID
     assert b"null pointer" in L.nafb_last_error()
