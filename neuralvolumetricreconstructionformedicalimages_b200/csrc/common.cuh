@@ -64,6 +64,25 @@ __device__ __forceinline__ uint32_t grid_entry2(const LevelParams &lp, uint32_t 
     return wrap_index(lp.hashed ? hashed : linear, lp);
 }
 
+// The 8 corner entries of one cell with the per-axis terms hoisted: hash(x, y, z) = x ^ y*P1 ^ z*P2 and the linear index
+// x + y*s1 + z*s2 are both "combine(a[dx], b[dy], c[dz])", and (y+1)*m = y*m + m in uint32 arithmetic -- 2 multiplies
+// per level instead of 16+.  Same uint32 wrap-around as get_grid_index (hashencoder.cu:55-74): bit-identical indices.
+struct CellTerms {
+    uint32_t a[2], b[2], c[2];
+};
+__device__ __forceinline__ CellTerms cell_terms3(const LevelParams &lp, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t m1 = lp.hashed ? 19349663u : lp.s1, m2 = lp.hashed ? 83492791u : lp.s2;
+    CellTerms t;
+    t.a[0] = x; t.a[1] = x + 1u;
+    t.b[0] = y * m1; t.b[1] = t.b[0] + m1;
+    t.c[0] = z * m2; t.c[1] = t.c[0] + m2;
+    return t;
+}
+__device__ __forceinline__ uint32_t cell_entry(const LevelParams &lp, const CellTerms &t, uint32_t dx, uint32_t dy, uint32_t dz) {
+    const uint32_t h = t.a[dx] ^ t.b[dy] ^ t.c[dz], l = t.a[dx] + t.b[dy] + t.c[dz];
+    return wrap_index(lp.hashed ? h : l, lp);
+}
+
 // pos = fma(x, scale, 0.5); g = floor(pos); f = pos - g   (hashencoder.cu:106-111).
 __device__ __forceinline__ void locate(float x01, float scale, uint32_t &g, float &f) {
     const float pos = __fmaf_rn(x01, scale, 0.5f);

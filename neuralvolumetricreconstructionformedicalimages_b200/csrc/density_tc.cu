@@ -77,11 +77,11 @@ __device__ __forceinline__ void gather_half(const GridParams &gp, const float (&
 #pragma unroll
         for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
         const uint32_t par = addr_parity8(tab);
+        const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
         float v[8][C];
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j)   // (y, z) corner; the two x-neighbours share one access when adjacent + aligned
-            load_entry_pair<C>(tab, par, grid_entry3(lp, g[0], g[1] + (j & 1u), g[2] + (j >> 1)),
-                               grid_entry3(lp, g[0] + 1u, g[1] + (j & 1u), g[2] + (j >> 1)), v[2 * j], v[2 * j + 1]);
+            load_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v[2 * j], v[2 * j + 1]);
         float res[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) res[c] = 0.f;
@@ -127,6 +127,7 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
     locate(x0, lp.scale, g[0], f[0]);
     locate(x1, lp.scale, g[1], f[1]);
     locate(x2, lp.scale, g[2], f[2]);
+    const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
     umma::tmem_wait_ld();
     if (try_agg) {
         // runs of equal cells among consecutive lanes (invalid lanes: a run of their own, never issued)
@@ -159,8 +160,8 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
             if (head && valid) {
 #pragma unroll
                 for (uint32_t j = 0; j < 4; ++j)
-                    red_add_entry_pair<C>(tab, par, grid_entry3(lp, g[0], g[1] + (j & 1u), g[2] + (j >> 1)),
-                                          grid_entry3(lp, g[0] + 1u, g[1] + (j & 1u), g[2] + (j >> 1)), v[2 * j], v[2 * j + 1]);
+                    red_add_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v[2 * j],
+                                          v[2 * j + 1]);
             }
             return;
         }
@@ -175,8 +176,7 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
                 v0[c] = __fmul_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.0f, f[0]), (j & 1u) ? f[1] : __fsub_rn(1.0f, f[1])), (j >> 1) ? f[2] : __fsub_rn(1.0f, f[2])), ge[c]);
                 v1[c] = __fmul_rn(__fmul_rn(__fmul_rn(f[0], (j & 1u) ? f[1] : __fsub_rn(1.0f, f[1])), (j >> 1) ? f[2] : __fsub_rn(1.0f, f[2])), ge[c]);
             }
-            red_add_entry_pair<C>(tab, par, grid_entry3(lp, g[0], g[1] + (j & 1u), g[2] + (j >> 1)),
-                                  grid_entry3(lp, g[0] + 1u, g[1] + (j & 1u), g[2] + (j >> 1)), v0, v1);
+            red_add_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v0, v1);
         }
     }
 }
@@ -197,10 +197,11 @@ __device__ __noinline__ void gather_half_to_smem(const LevelParams *__restrict__
         locate(x0, lp.scale, g[0], f[0]);
         locate(x1, lp.scale, g[1], f[1]);
         locate(x2, lp.scale, g[2], f[2]);
+        const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
         float v[8][C];
 #pragma unroll
         for (uint32_t idx = 0; idx < 8; ++idx)
-            load_entry<C>(tab, grid_entry3(lp, g[0] + (idx & 1u), g[1] + ((idx >> 1) & 1u), g[2] + (idx >> 2)), v[idx]);
+            load_entry<C>(tab, cell_entry(lp, ct, idx & 1u, (idx >> 1) & 1u, idx >> 2), v[idx]);
         float res[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) res[c] = 0.f;

@@ -1,0 +1,75 @@
+"""Reconstruction-quality parity (BASELINE.json: "PSNR/SSIM after a fixed number of iterations must match within 0.1 dB").
+
+The fused engine and the CPU oracle (the restated reference: render + DensityNetwork + hash grid + chunked masked MSE +
+torch.optim.Adam) train the same network on the same analytic phantom, the same ray batches and the same sampling
+uniforms for a fixed number of iterations; both reconstructions are scored against the phantom with the reference's 3-D
+PSNR (src/utils/util.py:55-84 as restated in oracle/naf.py).  The two training runs differ only by rounding (summation
+order of the float atomics, bf16x3 products), so the scores must agree to well under 0.1 dB.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import phantom as PH
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder import get_encoder
+    from neuralvolumetricreconstructionformedicalimages_b200.engine import NAFEngine
+    from neuralvolumetricreconstructionformedicalimages_b200.network import get_network
+
+from oracle import hashgrid as oh
+from oracle import naf
+
+DEV = "cuda"
+STEPS, N_RAYS, N_SAMPLES, LOG2_T = 150, 512, 64, 15
+
+
+def test_psnr_after_fixed_iterations_matches_oracle():
+    torch.manual_seed(0)
+    rng = np.random.default_rng(0)
+    data = G.chest50_like(n_voxel=32, n_detector=64, n_proj=20)
+    geo = G.ConeGeometry(data)
+    ells = PH.default_ellipsoids(float(geo.sVoxel[0]) / 2)
+    vol_gt = PH.phantom_volume(geo, ells)
+    rays_all = G.rays_with_near_far(data["angles"], geo, "cpu").reshape(-1, 8)
+    projs_all = PH.phantom_projections(rays_all, ells)
+    assert float(projs_all.max()) > 0.01
+
+    enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=LOG2_T)
+    net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(DEV)
+    o_enc = oh.OracleHashEncoder(3, 16, 2, 16, LOG2_T, use_ref=False, normalise="mul_recip")
+    o_net = naf.OracleDensityNetwork(o_enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid")
+    with torch.no_grad():
+        o_enc.embeddings.copy_(enc.embeddings.cpu())
+        for a, b in zip(o_net.layers, net.layers):
+            a.weight.copy_(b.weight.cpu())
+            a.bias.copy_(b.bias.cpu())
+    opt = torch.optim.Adam(o_net.parameters(), lr=2e-3, betas=(0.9, 0.999))
+    eng = NAFEngine(net, lr=2e-3, n_samples=N_SAMPLES, perturb=True, loss_chunk=200, use_cuda_graph=True)
+
+    losses = []
+    for it in range(STEPS):
+        pix = torch.from_numpy(rng.choice(rays_all.shape[0], N_RAYS, replace=False))
+        rays, projs = rays_all[pix], projs_all[pix]
+        mask = torch.from_numpy(rng.uniform(0, 1, N_RAYS) > 0.02)
+        t_rand = torch.from_numpy(rng.uniform(0, 1, (N_RAYS, N_SAMPLES)).astype(np.float32))
+        lc = eng.train_step(rays.to(DEV), projs.to(DEV), mask.to(DEV).to(torch.uint8), t_rand.to(DEV))
+        lo = naf.train_step(o_net, opt, rays, projs, N_SAMPLES, True, t_rand=t_rand, mask=mask, chunk=200)
+        losses.append((float(lc.item()), float(lo.item())))
+    first, last = losses[0], losses[-1]
+    assert last[0] < 0.5 * first[0] and last[1] < 0.5 * first[1], (first, last)           # both actually train
+    np.testing.assert_allclose(last[0], last[1], rtol=0.05)
+
+    n = [int(v) for v in geo.nVoxel]
+    s_half = G.voxel_half_extent(geo)
+    vol_c = eng.voxel_query(n, s_half).cpu().numpy()
+    with torch.no_grad():
+        vox = torch.from_numpy(G.get_voxels(geo).astype(np.float32))
+        vol_o = naf.run_network(vox, o_net, 409600).squeeze(-1).numpy()
+    psnr_c, psnr_o = naf.psnr_3d(vol_c, vol_gt), naf.psnr_3d(vol_o, vol_gt)
+    print(f"PSNR_3d after {STEPS} iterations: engine {psnr_c:.3f} dB, oracle {psnr_o:.3f} dB; loss {last}")
+    assert abs(psnr_c - psnr_o) <= 0.1, (psnr_c, psnr_o)
+    # and the two volumes themselves agree closely
+    assert naf.psnr_3d(vol_c, vol_o) > 40.0
