@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 4
+#define NAFB_ABI_VERSION 5
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -124,6 +124,18 @@ typedef struct nafb_sampler {
     uint32_t n_rays;
     uint32_t n_samples;
     int32_t perturb;
+    /* NAFB_SRC_RAYS with rays == NULL: the rays are GENERATED in-kernel from detector pixels (reference
+     * src/dataset/tigre.py:402-456 get_rays, :463-528 get_rays2, poses of :530-572), bit-identical to the reference's
+     * fp32 torch arithmetic:  uu = ((col + .5) - W/2) * du + u0,  cone: d = R.[uu/DSD, vv/DSD, 1], o = t;
+     * parallel: d = R.[0,0,1], o = R.[uu,vv,0] + t;  near / far = the global pair of tigre.py:575-586. */
+    const float *poses;      /* [n_proj, 12] fp32: rotation (3x3 row-major) then translation, fp32 cast of angle2pose */
+    const int32_t *pixels;   /* [N, 3]: projection index, detector row, detector column */
+    uint32_t det_w, det_h;   /* nDetector[0], nDetector[1] */
+    float det_du, det_dv;    /* dDetector (metres) */
+    float det_u0, det_v0;    /* offDetector (metres) */
+    float det_dsd;           /* source-detector distance (metres); cone beam only */
+    float det_near, det_far;
+    int32_t det_parallel;    /* 0: cone beam, 1: parallel beam */
     /* NAFB_SRC_VOXELS: reference src/dataset/tigre.py:388-400 */
     uint32_t n1, n2, n3;     /* full lattice */
     uint32_t i0, i1;         /* slab [i0, i1) of the outermost index handled by this call */
@@ -164,6 +176,8 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
  * sum_i |pts[r,i+1]-pts[r,i]|_1 per ray (render.py:16-28) when non-NULL. */
 int nafb_sample_points(const nafb_sampler *smp, float *z_vals, float *pts, float *tv_partial,
                        nafb_stream_t stream);
+/* rays_out [N,8] for the detector pixels of the sampler (the in-kernel generator written out). */
+int nafb_generate_rays(const nafb_sampler *smp, float *rays_out, nafb_stream_t stream);
 /* raw2outputs (render.py:178-212), raw [N,S,out_dim] (channel 0 integrated): acc [N];
  * absdiff [N,S] = (1e-10, |raw_i - raw_{i-1}|) when non-NULL (the un-normalised `weights`). */
 int nafb_ray_integral_forward(const float *raw, uint32_t out_dim, const float *z_vals, const float *rays,

@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnafb200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 NAFB_MAX_LEVELS = 32
 NAFB_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
@@ -45,6 +45,9 @@ class Sampler(ctypes.Structure):
     _fields_ = [("pts", ctypes.c_void_p), ("n_points", u64), ("rays", ctypes.c_void_p), ("t_rand", ctypes.c_void_p),
                 ("rng_state", ctypes.c_void_p),
                 ("n_rays", u32), ("n_samples", u32), ("perturb", i32),
+                ("poses", ctypes.c_void_p), ("pixels", ctypes.c_void_p), ("det_w", u32), ("det_h", u32),
+                ("det_du", ctypes.c_float), ("det_dv", ctypes.c_float), ("det_u0", ctypes.c_float), ("det_v0", ctypes.c_float),
+                ("det_dsd", ctypes.c_float), ("det_near", ctypes.c_float), ("det_far", ctypes.c_float), ("det_parallel", i32),
                 ("n1", u32), ("n2", u32), ("n3", u32), ("i0", u32), ("i1", u32),
                 ("s1", ctypes.c_double), ("s2", ctypes.c_double), ("s3", ctypes.c_double),
                 ("bound", ctypes.c_float), ("clamp", ctypes.c_float)]
@@ -80,6 +83,7 @@ _SIGNATURES = {
     "nafb_density_backward_workspace_bytes": (u64, [ctypes.POINTER(Mlp)]),
     "nafb_density_backward": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), ctypes.c_int, c_f32p, c_f32p, ctypes.POINTER(MlpGrads), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nafb_sample_points": (ctypes.c_int, [ctypes.POINTER(Sampler), c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
+    "nafb_generate_rays": (ctypes.c_int, [ctypes.POINTER(Sampler), c_f32p, ctypes.c_void_p]),
     "nafb_ray_integral_forward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_ray_integral_backward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_mse_loss": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, u32, u32, ctypes.c_float, c_f32p, c_f32p, ctypes.c_int, ctypes.c_void_p]),

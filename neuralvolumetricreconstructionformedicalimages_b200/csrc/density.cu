@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(TILE, 3) k_density_fwd(const GridParams gp, co
                 if (valid) {
                     r = (uint32_t)(p / sp.n_samples);
                     const uint32_t i = (uint32_t)(p - (uint64_t)r * sp.n_samples);
-                    const RayRegs R = load_ray(sp.rays, r);
+                    const RayRegs R = load_ray(sp, r);
                     contrib = __fmul_rn(y, ray_delta(sp, R, r, i));   // render.py:201
                     if (z_out)
                         z_out[p] = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(TILE, 2) k_density_bwd(const GridParams gp, co
             if constexpr (SRC == NAFB_SRC_RAYS) {
                 const uint32_t r = (uint32_t)(p / sp.n_samples);
                 const uint32_t i = (uint32_t)(p - (uint64_t)r * sp.n_samples);
-                const RayRegs R = load_ray(sp.rays, r);
+                const RayRegs R = load_ray(sp, r);
                 dsig = __fmul_rn(__ldg(dsig_or_dacc + r), ray_delta(sp, R, r, i));
             } else {
                 dsig = __ldg(dsig_or_dacc + p);

@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, c
                     if (valid) {
                         ray = (uint32_t)(p / sp.n_samples);
                         const uint32_t i = (uint32_t)(p - (uint64_t)ray * sp.n_samples);
-                        const RayRegs R = load_ray(sp.rays, ray);
+                        const RayRegs R = load_ray(sp, ray);
                         contrib = __fmul_rn(y, ray_delta(sp, R, ray, i));  // render.py:201
                         if (z_out)
                             z_out[p] = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(NT_B, 2) k_density_bwd_tc(const GridParams gp,
             if constexpr (SRC == NAFB_SRC_RAYS) {
                 const uint32_t ray = (uint32_t)(p / sp.n_samples);
                 const uint32_t i = (uint32_t)(p - (uint64_t)ray * sp.n_samples);
-                const RayRegs R = load_ray(sp.rays, ray);
+                const RayRegs R = load_ray(sp, ray);
                 dsig = __fmul_rn(__ldg(dsig_or_dacc + ray), ray_delta(sp, R, ray, i));
             } else {
                 dsig = __ldg(dsig_or_dacc + p);

@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(128) k_sample_points(const SamplerParams sp, f
                                                        float *__restrict__ tv_partial) {
     const uint32_t r = blockIdx.x;
     const uint32_t S = sp.n_samples;
-    const RayRegs R = load_ray(sp.rays, r);
+    const RayRegs R = load_ray(sp, r);
     const Jitter tr = jitter_for(sp, r);
     float tv = 0.f;
     for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
@@ -77,6 +77,16 @@ __global__ void __launch_bounds__(256) k_ray_integral_bwd(const float *__restric
     for (uint32_t c = 1; c < out_dim; ++c) draw[p * out_dim + c] = 0.f;
 }
 
+// rays [N,8] of N detector pixels (the in-kernel generator of sampler.cuh written out: dataset initialisation, tests)
+__global__ void __launch_bounds__(256) k_generate_rays(const SamplerParams sp, float *__restrict__ rays_out) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= sp.n_rays) return;
+    const RayRegs R = make_ray(sp, r);
+    float4 *o = reinterpret_cast<float4 *>(rays_out) + 2 * (size_t)r;
+    o[0] = make_float4(R.o[0], R.o[1], R.o[2], R.d[0]);
+    o[1] = make_float4(R.d[1], R.d[2], R.near, R.far);
+}
+
 // Single block, deterministic: loss = sum_chunks mean_{valid in chunk} (target - pred)^2   (train.py:69-127, loss.py:26-46).
 // One warp per chunk (all chunks of a group in flight at once); the chunk means are then added in chunk order by one
 // thread, as the reference's python loop does.  `zero_pred`: pred is cleared after it has been consumed (the fused engine
@@ -135,6 +145,22 @@ int nafb_sample_points(const nafb_sampler *smp, float *z_vals, float *pts, float
     if (P == 0) return NAFB_OK;
     k_sample_points<<<sp.n_rays, 128, 0, (cudaStream_t)stream>>>(sp, z_vals, pts, tv_partial);
     NAFB_CHECK_LAUNCH("sample_points");
+    return NAFB_OK;
+}
+
+int nafb_generate_rays(const nafb_sampler *smp, float *rays_out, nafb_stream_t stream) {
+    if (!smp || !smp->pixels || !smp->poses || !rays_out) NAFB_FAIL(NAFB_ERR_INVALID, "generate_rays: pixels, poses and rays_out are required");
+    nafb_sampler tmp = *smp;
+    tmp.rays = nullptr;
+    if (tmp.n_samples == 0) tmp.n_samples = 1;
+    tmp.perturb = 0;
+    SamplerParams sp;
+    uint64_t P = 0;
+    int rc = nafb_make_sampler_params(&tmp, NAFB_SRC_RAYS, &sp, &P);
+    if (rc) return rc;
+    if (sp.n_rays == 0) return NAFB_OK;
+    k_generate_rays<<<(sp.n_rays + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sp, rays_out);
+    NAFB_CHECK_LAUNCH("generate_rays");
     return NAFB_OK;
 }
 

@@ -13,6 +13,12 @@ struct SamplerParams {
     const float *rays;
     const float *t_rand;
     const uint32_t *rng_state;   // device nafb_step_state (step, seed): in-kernel uniforms when t_rand is NULL
+    // in-kernel ray generation (RAYS source with `pixels` instead of `rays`): tigre.py:402-456 / :463-528
+    const float *poses;          // [n_proj, 12] fp32: R (3x3 row-major) | t (3)
+    const int32_t *pixels;       // [N, 3]: projection, detector row, detector column
+    float det_w2, det_h2;        // fl(W / 2), fl(H / 2)
+    float det_du, det_dv, det_u0, det_v0, det_dsd, det_near, det_far;
+    int32_t det_parallel;
     uint32_t n_rays, n_samples;
     int32_t perturb;
     uint32_t n1, n2, n3, i0, i1;
@@ -95,6 +101,47 @@ __device__ __forceinline__ float voxel_coord(uint32_t i, uint32_t n, double s) {
     return (float)__dadd_rn(__dmul_rn((double)i, step), -s);
 }
 
+// Ray of detector pixel (projection, row, col), generated in-kernel with the arithmetic of the reference's dataset code
+// as torch evaluates it on fp32 tensors, one rounding per elementary op (tigre.py:428-447 / :486-501, poses :530-572):
+//   uu = ((col + 0.5) - W/2) * dDet[0] + offDet[0]      vv likewise with rows
+//   cone:      d = R . [uu/DSD, vv/DSD, 1],  o = t       parallel:  d = R . [0, 0, 1],  o = R . [uu, vv, 0] + t
+// and the 3x3 product as torch.matmul rounds it: ((r0*x + r1*y) + r2*z), no fused multiply-add.  near / far: the global
+// pair of tigre.py:575-586.  tests/test_gpu_parity.py compares with the reference's own rays bit for bit.
+__device__ __forceinline__ float dot3_lr(float r0, float r1, float r2, float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(r0, x), __fmul_rn(r1, y)), __fmul_rn(r2, z));
+}
+__device__ __forceinline__ RayRegs make_ray(const SamplerParams &sp, uint32_t r) {
+    const int32_t pj = __ldg(sp.pixels + 3 * (size_t)r), row = __ldg(sp.pixels + 3 * (size_t)r + 1), col = __ldg(sp.pixels + 3 * (size_t)r + 2);
+    const float *__restrict__ T = sp.poses + 12 * (size_t)pj;
+    float M[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) M[i] = __ldg(T + i);
+    const float uu = __fadd_rn(__fmul_rn(__fsub_rn(__fadd_rn((float)col, 0.5f), sp.det_w2), sp.det_du), sp.det_u0);
+    const float vv = __fadd_rn(__fmul_rn(__fsub_rn(__fadd_rn((float)row, 0.5f), sp.det_h2), sp.det_dv), sp.det_v0);
+    RayRegs R;
+    if (sp.det_parallel) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            R.d[k] = dot3_lr(M[3 * k], M[3 * k + 1], M[3 * k + 2], 0.f, 0.f, 1.f);
+            R.o[k] = __fadd_rn(dot3_lr(M[3 * k], M[3 * k + 1], M[3 * k + 2], uu, vv, 0.f), M[9 + k]);
+        }
+    } else {
+        const float x = __fdiv_rn(uu, sp.det_dsd), y = __fdiv_rn(vv, sp.det_dsd);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            R.d[k] = dot3_lr(M[3 * k], M[3 * k + 1], M[3 * k + 2], x, y, 1.f);
+            R.o[k] = M[9 + k];
+        }
+    }
+    R.near = sp.det_near; R.far = sp.det_far;
+    R.norm = sqrtf(__fmaf_rn(R.d[2], R.d[2], __fmaf_rn(R.d[1], R.d[1], __fmul_rn(R.d[0], R.d[0]))));
+    return R;
+}
+// the ray of index r of the launch: from the rays tensor, or generated from its detector pixel
+__device__ __forceinline__ RayRegs load_ray(const SamplerParams &sp, uint32_t r) {
+    return sp.pixels ? make_ray(sp, r) : load_ray(sp.rays, r);
+}
+
 __device__ __forceinline__ Jitter jitter_for(const SamplerParams &sp, uint32_t ray) {
     Jitter j;
     j.row = sp.t_rand ? sp.t_rand + (size_t)ray * sp.n_samples : nullptr;
@@ -116,7 +163,7 @@ __device__ __forceinline__ void fetch_point(const SamplerParams &sp, uint64_t p,
         x[2] = __ldg(sp.pts + 3 * p + 2);
     } else if constexpr (SRC == NAFB_SRC_RAYS) {
         const uint32_t r = (uint32_t)(p / sp.n_samples), i = (uint32_t)(p - (uint64_t)r * sp.n_samples);
-        const RayRegs R = load_ray(sp.rays, r);
+        const RayRegs R = load_ray(sp, r);
         const float z = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0, jitter_for(sp, r));
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[d] = ray_point(R.o[d], R.d[d], z, sp.clamp);
@@ -159,6 +206,10 @@ static inline int nafb_make_sampler_params(const nafb_sampler *s, int src, Sampl
     if (!s) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: null");
     SamplerParams p{};
     p.pts = s->pts; p.rays = s->rays; p.t_rand = s->t_rand; p.rng_state = s->rng_state;
+    p.poses = s->poses; p.pixels = s->pixels;
+    p.det_w2 = (float)((double)s->det_w / 2.0); p.det_h2 = (float)((double)s->det_h / 2.0);
+    p.det_du = s->det_du; p.det_dv = s->det_dv; p.det_u0 = s->det_u0; p.det_v0 = s->det_v0; p.det_dsd = s->det_dsd;
+    p.det_near = s->det_near; p.det_far = s->det_far; p.det_parallel = s->det_parallel;
     p.n_rays = s->n_rays; p.n_samples = s->n_samples; p.perturb = s->perturb;
     p.n1 = s->n1; p.n2 = s->n2; p.n3 = s->n3; p.i0 = s->i0; p.i1 = s->i1;
     p.s1 = s->s1; p.s2 = s->s2; p.s3 = s->s3;
@@ -174,7 +225,8 @@ static inline int nafb_make_sampler_params(const nafb_sampler *s, int src, Sampl
             break;
         case NAFB_SRC_RAYS:
             n = (uint64_t)s->n_rays * s->n_samples;
-            if (n && !s->rays) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: rays is null");
+            if (n && !s->rays && !(s->pixels && s->poses)) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: rays is null (and no pixels + poses to generate them from)");
+            if (s->rays) p.pixels = nullptr;   // an explicit rays tensor wins
             if (n && s->perturb && !s->t_rand && !s->rng_state)
                 NAFB_FAIL(NAFB_ERR_INVALID, "nafb_sampler: perturb needs t_rand (or rng_state for in-kernel uniforms)");
             break;

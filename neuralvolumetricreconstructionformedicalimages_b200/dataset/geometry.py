@@ -116,3 +116,22 @@ def chest50_like(n_voxel=128, n_detector=256, n_proj=50) -> dict:
     return dict(DSD=1500.0, DSO=1000.0, nDetector=[n_detector, n_detector], dDetector=[1.0, 1.0], nVoxel=[n_voxel] * 3,
                 dVoxel=[128.0 / n_voxel] * 3, offOrigin=[0, 0, 0], offDetector=[0, 0], accuracy=0.5, mode="cone", filter=None,
                 angles=np.linspace(0, np.pi, n_proj + 1)[:-1])
+
+
+# ----------------------------------------------------------------------------- in-kernel ray generation
+def pose_table(angles, geo: ConeGeometry, device="cpu") -> torch.Tensor:
+    """[P, 12] fp32: rotation (3x3 row-major) | translation of every projection -- the fp32 cast of angle2pose that
+    get_rays applies (``torch.Tensor(pose)``, tigre.py:479).  Input of the kernels' pixel source (nafb_sampler.poses)."""
+    out = np.stack([np.concatenate([angle2pose(geo.DSO, float(a), geo.tilt_angle)[:3, :3].reshape(-1),
+                                    angle2pose(geo.DSO, float(a), geo.tilt_angle)[:3, 3]]) for a in angles])
+    return torch.from_numpy(out.astype(np.float32)).to(device).contiguous()
+
+
+def detector_fields(geo: ConeGeometry) -> dict:
+    """The scalar fields of nafb_sampler that describe the detector; every value is the fp32 cast torch applies when the
+    reference multiplies / adds these numpy float64 scalars to fp32 tensors (tigre.py:428-429, 434, 248-255)."""
+    near, far = get_near_far(geo)
+    f = lambda v: float(np.float32(v))
+    return dict(det_w=int(geo.nDetector[0]), det_h=int(geo.nDetector[1]), det_du=f(geo.dDetector[0]), det_dv=f(geo.dDetector[1]),
+                det_u0=f(geo.offDetector[0]), det_v0=f(geo.offDetector[1]), det_dsd=f(geo.DSD), det_near=f(near), det_far=f(far),
+                det_parallel=1 if geo.mode == "parallel" else 0)

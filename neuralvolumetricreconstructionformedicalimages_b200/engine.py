@@ -258,18 +258,34 @@ class NAFEngine:
         self.state[_lib.STATE_STEP : _lib.STATE_STEP + 1] = torch.tensor([self.step_count], dtype=torch.int32)
 
     # ------------------------------------------------------------------ one training step
-    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None, stash=None, par=0):
+    def set_geometry(self, angles, geo):
+        """Scanner geometry for the pixel source: the kernels generate the rays of (projection, row, col) themselves
+        (reference src/dataset/tigre.py:402-528) instead of reading a [N,8] rays tensor."""
+        from .dataset import geometry as G
+        self.poses = G.pose_table(angles, geo, self.device)
+        self.det = G.detector_fields(geo)
+
+    def _ray_sampler(self, rays, pixels, t_rand):
+        """nafb_sampler of a ray batch: explicit rays [N,8], or detector pixels [N,3] (needs set_geometry)."""
+        kw = dict(t_rand=t_rand.data_ptr() if t_rand is not None else None,
+                  rng_state=self.state.data_ptr() if (self.perturb and t_rand is None) else None,
+                  n_samples=self.n_samples, perturb=int(self.perturb))
+        if pixels is not None:
+            if getattr(self, "poses", None) is None:
+                raise RuntimeError("pixel batches need NAFEngine.set_geometry(angles, geo) first")
+            return self.meta.sampler(pixels=pixels.data_ptr(), poses=self.poses.data_ptr(), n_rays=pixels.shape[0], **self.det, **kw)
+        return self.meta.sampler(rays=rays.data_ptr(), n_rays=rays.shape[0], **kw)
+
+    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None, stash=None, par=0, pixels=None):
         """density_fwd -> mse_loss -> density_bwd (+ reduce).  t_rand None: the sampler draws its uniforms in-kernel."""
         L_ = _lib.lib()
         tm = timer or _NoTimer()
-        N = rays.shape[0]
+        N = pixels.shape[0] if pixels is not None else rays.shape[0]
         # acc is zero on entry: allocated zeroed, and mse_loss clears it after reading (zero_pred)
         grid = self.meta.grid(self.table)
         mlp = self.meta.mlp(self.mlp_params)
         explicit = self.perturb and t_rand is not None
-        smp = self.meta.sampler(rays=rays.data_ptr(), t_rand=t_rand.data_ptr() if explicit else None,
-                                rng_state=self.state.data_ptr() if (self.perturb and not explicit) else None, n_rays=N,
-                                n_samples=self.n_samples, perturb=int(self.perturb))
+        smp = self._ray_sampler(rays, pixels, t_rand if explicit else None)
         st = _lib.stream_ptr()
         with tm("density_fwd"):
             _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, None, _lib.ptr(acc),
@@ -279,8 +295,7 @@ class NAFEngine:
             _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), 1, st))
         with tm("density_bwd"):
             gv = self._grad_views[par]
-            density_backward(self.meta, self.table, self.mlp_params, dacc, gv[0], gv[1:], rays=rays, t_rand=t_rand if explicit else None,
-                             n_samples=self.n_samples, perturb=self.perturb, stash=stash, rng_state=None if explicit else self.state)
+            density_backward(self.meta, self.table, self.mlp_params, dacc, gv[0], gv[1:], sampler=smp, n_points=N * self.n_samples, stash=stash)
 
     def _optimizer_kernel(self, par, timer=None):
         """Peer mode: the fused exchange kernel.  Otherwise the dense Adam kernel.  Both take step / lr from the device state
@@ -296,8 +311,9 @@ class NAFEngine:
                                              _lib.ptr(self.exp_avg_sq), self.n_params, self.betas[0], self.betas[1], self.eps,
                                              1.0 / self.world_size, 1, _lib.ptr(self.state), _lib.stream_ptr()))
 
-    def _whole_step(self, s, par, timer=None, t_rand=None, with_optimizer=True):
-        self._step_kernels(s["rays"], s["projs"], s["mask"], t_rand, s["loss"], s["dacc"], s["acc"], timer, stash=s["stash"], par=par)
+    def _whole_step(self, s, par, timer=None, t_rand=None, with_optimizer=True, use_pixels=False):
+        self._step_kernels(None if use_pixels else s["rays"], s["projs"], s["mask"], t_rand, s["loss"], s["dacc"], s["acc"], timer,
+                           stash=s["stash"], par=par, pixels=s["pixels"] if use_pixels else None)
         if with_optimizer:
             self._finish_step(par, timer)
 
@@ -310,10 +326,15 @@ class NAFEngine:
     # kernels of this library launched by one train_step (density_fwd, mse_loss, density_bwd, reduce_partials, adam / adam_exchange)
     LAUNCHES_PER_STEP = 5
 
-    def _load_inputs(self, s, rays, projs, mask, t_rand):
+    def _load_inputs(self, s, rays, projs, mask, t_rand, pixels=None):
         """Inputs -> the static buffers the graph reads (device tensors, or pinned host tensors: one H2D copy each)."""
         N = s["rays"].shape[0]
-        s["rays"].copy_(rays.reshape(N, 8), non_blocking=True)
+        if pixels is not None:
+            if s["pixels"] is None:
+                s["pixels"] = torch.zeros(N, 3, device=self.device, dtype=torch.int32)
+            s["pixels"].copy_(pixels.reshape(N, 3), non_blocking=True)
+        else:
+            s["rays"].copy_(rays.reshape(N, 8), non_blocking=True)
         s["projs"].copy_(projs.reshape(N), non_blocking=True)
         if mask is not None:
             s["mask"].copy_(mask.reshape(N), non_blocking=True)
@@ -343,36 +364,38 @@ class NAFEngine:
             nb = stash_bytes(self.meta, self.table, self.mlp_params, N * self.n_samples) if self.use_stash else 0
             s = dict(rays=torch.zeros(N, 8, device=d), projs=torch.zeros(N, device=d),
                      stash=torch.empty(nb, dtype=torch.uint8, device=d) if nb else None,
-                     mask=torch.ones(N, device=d, dtype=torch.uint8) if with_mask else None, t_rand=None,
+                     mask=torch.ones(N, device=d, dtype=torch.uint8) if with_mask else None, t_rand=None, pixels=None,
                      loss=torch.zeros(2, device=d), dacc=torch.zeros(N, device=d), acc=torch.zeros(N, device=d))
             self._static[key] = s
         return s
 
-    def train_step(self, rays, projs, mask=None, t_rand=None):
-        """One optimisation step.  rays [N,8], projs [N] (+ optional uint8/bool mask [N]) on the device or in pinned host
+    def train_step(self, rays, projs, mask=None, t_rand=None, pixels=None):
+        """One optimisation step.  rays [N,8] -- or rays=None and pixels [N,3] int32 (projection, row, col; the kernels then
+        generate the rays, see set_geometry) --, projs [N] (+ optional uint8/bool mask [N]) on the device or in pinned host
         memory; t_rand [N,S]: explicit uniforms of render.py:99 (parity runs) -- by default the kernels draw them themselves.
         Returns the loss as a 0-dim device tensor (no host synchronisation)."""
-        N = rays.shape[0]
+        use_pixels = pixels is not None
+        N = pixels.shape[0] if use_pixels else rays.shape[0]
         s = self._get_static(N, mask is not None)
         with torch.cuda.device(self.device):
-            tr = self._load_inputs(s, rays, projs, mask, t_rand)
+            tr = self._load_inputs(s, rays, projs, mask, t_rand, pixels)
             par = self._parity()
-            key = (N, mask is not None, par, tr is not None)
+            key = (N, mask is not None, par, tr is not None, use_pixels)
             # one graph per (shape, parity) holds the whole iteration; only an NCCL all-reduce (+ the Adam after it) stays outside
             in_graph = not (self.world_size > 1 and self.px is None)
             if not self.use_cuda_graph:
-                self._whole_step(s, par, None, tr)
+                self._whole_step(s, par, None, tr, use_pixels=use_pixels)
             else:
                 g = self._graphs.get(key)
                 if g is None and self._eager_runs.get(key, 0) < 1:
                     # first use of a shape: run eagerly (kernel attributes / lazy module loading must not happen under capture)
                     self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
-                    self._whole_step(s, par, None, tr)
+                    self._whole_step(s, par, None, tr, use_pixels=use_pixels)
                 else:
                     if g is None:
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g):
-                            self._whole_step(s, par, None, tr, with_optimizer=in_graph)
+                            self._whole_step(s, par, None, tr, with_optimizer=in_graph, use_pixels=use_pixels)
                         self._graphs[key] = g   # capture does not execute: the replay below performs this step
                     g.replay()
                     if not in_graph:

@@ -119,15 +119,18 @@ def density_forward(meta: NetMeta, table, params, *, pts=None, rays=None, t_rand
 
 
 def density_backward(meta: NetMeta, table, params, dsig_or_dacc, grad_table, grad_params, *, pts=None, rays=None, t_rand=None,
-                     n_samples=0, perturb=False, stash=None, rng_state=None):
+                     n_samples=0, perturb=False, stash=None, rng_state=None, sampler=None, n_points=None):
     """Accumulates into grad_table / grad_params (list aligned with params; entries may be None).
-    `stash` is what density_forward(want_stash=True) returned for the same points, or None."""
+    `stash` is what density_forward(want_stash=True) returned for the same points, or None.
+    `sampler`: a ready nafb_sampler of the RAYS source (the engine passes the one its forward used) with `n_points`."""
     L_ = _lib.lib()
     dev = table.device
     grid = meta.grid(table)
     mlp = meta.mlp(params)
     grads = _lib.make_mlp_grads(grad_params[0::2], grad_params[1::2])
-    if pts is not None:
+    if sampler is not None:
+        smp, src = sampler, _lib.SRC_RAYS
+    elif pts is not None:
         smp = meta.sampler(pts=pts.data_ptr(), n_points=pts.shape[0])
         src = _lib.SRC_POINTS
     else:
@@ -137,7 +140,7 @@ def density_backward(meta: NetMeta, table, params, dsig_or_dacc, grad_table, gra
         src = _lib.SRC_RAYS
     ws = _workspace(mlp, dev)
     if stash is not None:
-        P = pts.shape[0] if pts is not None else rays.shape[0] * n_samples
+        P = n_points if sampler is not None else (pts.shape[0] if pts is not None else rays.shape[0] * n_samples)
         if stash.numel() != int(L_.nafb_density_stash_bytes(ctypes.byref(grid), ctypes.byref(mlp), P)):
             stash = None  # the arithmetic mode changed between forward and backward: recompute
     with torch.cuda.device(dev):

@@ -321,6 +321,62 @@ def test_density_ragged_and_range(mlp_mode):
     assert net(torch.zeros(4, 5, 3, device=DEV)).shape == (4, 5, 1)
 
 
+# ----------------------------------------------------------------------------- in-kernel ray generation
+@pytest.mark.parametrize("mode,tilt", [("cone", 0), ("parallel", 29), ("parallel", 0), ("cone", 10)])
+def test_generated_rays_bit_identical_to_reference(golden, mode, tilt):
+    """nafb_generate_rays (the generator the fused kernels use for pixel batches) against the rays the reference's
+    get_rays produced (tigre.py:402-456) for every pixel of 6 projections: bit-exact."""
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
+    fx = golden("geometry.npz")
+    base = dict(DSD=1500.0, DSO=1000.0, nDetector=[10, 6], dDetector=[1.5, 2.0], nVoxel=[8, 6, 4], dVoxel=[1.0, 2.0, 1.5],
+                offOrigin=[0, 0, 0], offDetector=[0.5, -1.0], accuracy=0.5, filter=None)
+    geo = G.ConeGeometry(dict(base, mode=mode, tilt_angle=tilt))
+    ref = fx[f"rays_{mode}_t{tilt}"]                                  # [P, H, W, 6]
+    P, H, W, _ = ref.shape
+    pj, row, col = np.meshgrid(np.arange(P), np.arange(H), np.arange(W), indexing="ij")
+    pixels = torch.from_numpy(np.stack([pj, row, col], -1).reshape(-1, 3).astype(np.int32)).to(DEV)
+    poses = G.pose_table(fx["angles"], geo, DEV)
+    smp = _lib.Sampler()
+    smp.pixels, smp.poses, smp.n_rays, smp.n_samples = pixels.data_ptr(), poses.data_ptr(), pixels.shape[0], 1
+    for k, v in G.detector_fields(geo).items():
+        setattr(smp, k, v)
+    out = torch.empty(pixels.shape[0], 8, device=DEV)
+    _lib.check(_lib.lib().nafb_generate_rays(ctypes.byref(smp), _lib.ptr(out), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(P, H, W, 8)
+    assert np.array_equal(bits(got[..., :6]), bits(ref))
+    near, far = G.get_near_far(geo)
+    assert np.all(got[..., 6] == np.float32(near)) and np.all(got[..., 7] == np.float32(far))
+
+
+def test_engine_pixel_batches_equal_ray_batches():
+    """A step fed with detector pixels (rays generated in the fused kernels) equals the step fed with the rays tensor."""
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
+    data = G.chest50_like(n_voxel=32, n_detector=64, n_proj=6)
+    geo = G.ConeGeometry(data)
+    # reference rays evaluated on the CPU (the fixtures' arithmetic; torch's CUDA kernels divide by a scalar as a multiply by
+    # its reciprocal and run the 3x3 products through cuBLAS, which differs from the CPU result by an ulp here and there)
+    rays_all = G.rays_with_near_far(data["angles"], geo, "cpu").to(DEV)  # [6, 64, 64, 8]
+    rng = np.random.default_rng(8)
+    N, S = 384, 96
+    pix = np.stack([rng.integers(0, 6, N), rng.integers(0, 64, N), rng.integers(0, 64, N)], -1).astype(np.int32)
+    pixels = torch.from_numpy(pix).to(DEV)
+    rays = rays_all[pix[:, 0], pix[:, 1], pix[:, 2]].contiguous()
+    projs = torch.from_numpy(rng.uniform(0, 0.05, N).astype(np.float32)).to(DEV)
+    t_rand = torch.from_numpy(rng.uniform(0, 1, (N, S)).astype(np.float32)).to(DEV)
+    res = []
+    for use_pixels in (False, True):
+        torch.manual_seed(0)
+        net = _chest_net(table_scale=0.3)
+        eng = NAFEngine(net, lr=1e-3, n_samples=S, perturb=True, loss_chunk=200, use_cuda_graph=False)
+        eng.set_geometry(data["angles"], geo)
+        for _ in range(2):
+            loss = eng.train_step(None if use_pixels else rays, projs, None, t_rand, pixels=pixels if use_pixels else None)
+        res.append((float(loss.item()), eng.flat_param.clone()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
+    np.testing.assert_allclose(res[0][1].cpu().numpy(), res[1][1].cpu().numpy(), rtol=0, atol=5e-6)
+
+
 # ----------------------------------------------------------------------------- render
 @both_modes
 def test_render_golden_chest(golden, mlp_mode):

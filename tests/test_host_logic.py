@@ -114,7 +114,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == _lib.exported_symbols()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.nafb_abi_version() == 4
+    assert L.nafb_abi_version() == 5
     # struct layouts agree with the C header (sizes computed by the C compiler)
     import subprocess
     import tempfile
@@ -131,3 +131,38 @@ def test_c_abi_exports_every_declared_symbol():
     g = _lib.Grid(1, offs.ctypes.data, 3, 3, 2, 4)
     assert L.nafb_hash_encode_forward(ctypes.byref(g), 1, 1, 4, 0, 0, None, None) == _lib.ERR_UNSUPPORTED
     assert L.nafb_last_error() == b"GridEncoding: C must be 1, 2, 4, or 8."
+
+
+def test_ptycho_mask_and_pixel_sampler(golden):
+    """get_ptycho_mask against the reference's output (util.py:196-205); PixelSampler draws valid pixels without replacement."""
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset.mask import PixelSampler, get_ptycho_mask
+    fx = golden("geometry.npz")
+    m = get_ptycho_mask(torch.from_numpy(fx["mask_in"].copy()), 0.007).numpy()
+    assert np.array_equal(m, fx["mask_out"])
+    rng = np.random.default_rng(4)
+    projs = torch.from_numpy(rng.uniform(0, 1, (3, 12, 17)).astype(np.float32))
+    projs[1, :4] = 0.0                                    # tigre.py:356: zero pixels are never drawn
+    full = torch.from_numpy(np.stack([fx["mask_in"]] * 3))
+    ps = PixelSampler(projs, full, 0.007)
+    assert np.array_equal(ps.mask[0].numpy().astype(bool), fx["mask_out"])
+    g = torch.Generator().manual_seed(0)
+    pix, pr, mk = ps.draw(1, 50, g)
+    assert pix.shape == (50, 3) and pix.dtype == torch.int32 and int(pix[:, 0].min()) == 1 and int(pix[:, 0].max()) == 1
+    flat = (pix[:, 1].long() * 17 + pix[:, 2].long()).numpy()
+    assert len(np.unique(flat)) == 50 and int(pix[:, 1].min()) >= 4      # no replacement, rows 0..3 (zero projection) excluded
+    assert torch.equal(pr, projs[1].reshape(-1)[flat]) and torch.equal(mk, ps.mask[1].reshape(-1)[flat])
+    with pytest.raises(ValueError):
+        ps.draw(1, 12 * 17, g)
+
+
+def test_pose_table_and_detector_fields(golden):
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
+    fx = golden("geometry.npz")
+    base = dict(DSD=1500.0, DSO=1000.0, nDetector=[10, 6], dDetector=[1.5, 2.0], nVoxel=[8, 6, 4], dVoxel=[1.0, 2.0, 1.5],
+                offOrigin=[0, 0, 0], offDetector=[0.5, -1.0], accuracy=0.5, filter=None)
+    geo = G.ConeGeometry(dict(base, mode="parallel", tilt_angle=29))
+    T = G.pose_table(fx["angles"], geo).numpy()
+    ref = fx["poses_parallel_t29"].astype(np.float32)
+    assert np.array_equal(T[:, :9].reshape(-1, 3, 3), ref[:, :3, :3]) and np.array_equal(T[:, 9:], ref[:, :3, 3])
+    d = G.detector_fields(geo)
+    assert d["det_w"] == 10 and d["det_h"] == 6 and d["det_parallel"] == 1 and d["det_du"] == float(np.float32(0.0015))
