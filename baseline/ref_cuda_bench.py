@@ -54,7 +54,7 @@ def main():
     sys.path.insert(0, ROOT)
     import bench
     dev = torch.device("cuda", 0)
-    rays_b, projs_b, mask_b, _ = bench.synthetic_batches(steps + warmup, dev, seed=1234)
+    _, rays_b, projs_b, mask_b, _ = bench.synthetic_batches(steps + warmup, dev, seed=1234)
     mask_b = mask_b.bool()
     for variant in ("chunked", "one_call"):
         torch.manual_seed(0)

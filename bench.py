@@ -100,25 +100,28 @@ def physical_gpu_index(local_rank):
 
 
 # --------------------------------------------------------------------------------------- synthetic data
-def synthetic_batches(n_batches, device, seed):
-    """Rays of a chest_50-like cone-beam scan (generated by the package's own geometry code) and
-    U(0, 0.05) projection values; every batch = 1024 distinct pixels of one projection + a pixel mask."""
+def synthetic_batches(n_batches, device, seed, rays_all_cpu=None):
+    """chest_50-like cone-beam scan (the package's own geometry code) with U(0, 0.05) projection values; every batch =
+    1024 distinct pixels of one projection (np.random.choice(replace=False), tigre.py:358) + a pixel mask.
+    Returns pixel batches [B,N,3] (projection, row, col), the same rays gathered from the host-generated ray table
+    [B,N,8], projections [B,N], masks [B,N] and (data, geo)."""
     from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
     data = G.chest50_like(N_VOXEL, DET, N_PROJ)
     geo = G.ConeGeometry(data)
-    rays_all = G.rays_with_near_far(data["angles"], geo, device)            # [50,256,256,8] fp32, 105 MB on the device
+    rays_all = G.rays_with_near_far(data["angles"], geo, "cpu").to(device)   # [50,256,256,8] fp32, 105 MB on the device
     gen = torch.Generator(device=device).manual_seed(seed)
     projs_all = torch.rand(N_PROJ, DET, DET, device=device, generator=gen) * 0.05
     mask_all = torch.rand(N_PROJ, DET, DET, device=device, generator=gen) > 0.02  # ~2 % of the pixels masked out
-    rays_b, projs_b, mask_b = [], [], []
+    pix_b, rays_b, projs_b, mask_b = [], [], [], []
     for b in range(n_batches):
         p = b % N_PROJ
-        pix = torch.randperm(DET * DET, device=device, generator=gen)[:N_RAYS]    # np.random.choice(replace=False), tigre.py:358
+        pix = torch.randperm(DET * DET, device=device, generator=gen)[:N_RAYS]
+        pix_b.append(torch.stack([torch.full_like(pix, p), pix // DET, pix % DET], 1).to(torch.int32))
         rays_b.append(rays_all[p].reshape(-1, 8)[pix])
         projs_b.append(projs_all[p].reshape(-1)[pix])
         mask_b.append(mask_all[p].reshape(-1)[pix])
     del rays_all
-    return torch.stack(rays_b), torch.stack(projs_b), torch.stack(mask_b).to(torch.uint8), geo
+    return torch.stack(pix_b), torch.stack(rays_b), torch.stack(projs_b), torch.stack(mask_b).to(torch.uint8), (data, geo)
 
 
 def build_engine(device):
@@ -301,6 +304,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=20)
+    ap.add_argument("--source", default="pixels", choices=["pixels", "rays"],
+                    help="pixels: batches are (projection,row,col) and the kernels generate the rays; rays: [N,8] ray tensors")
     ap.add_argument("--no-extra", action="store_true", help="skip the lamino / large-batch / voxel-query side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -324,9 +329,15 @@ def main():
 
     eng = build_engine(device)
     n_b = min(K + W, 256)
-    rays_b, projs_b, mask_b, geo = synthetic_batches(n_b, device, seed=1234 + rank)
+    pix_b, rays_b, projs_b, mask_b, (data, geo) = synthetic_batches(n_b, device, seed=1234 + rank)
+    eng.set_geometry(data["angles"], geo)
+    use_pixels = args.source == "pixels"     # the kernels generate the rays of (projection, row, col) themselves
+    in_b = pix_b if use_pixels else rays_b
     # host copies in pinned memory for the end-to-end leg
-    rays_h, projs_h, mask_h = rays_b.cpu().pin_memory(), projs_b.cpu().pin_memory(), mask_b.cpu().pin_memory()
+    in_h, projs_h, mask_h = in_b.cpu().pin_memory(), projs_b.cpu().pin_memory(), mask_b.cpu().pin_memory()
+
+    def step(inp, projs, mask):
+        return eng.train_step(None, projs, mask, pixels=inp) if use_pixels else eng.train_step(inp, projs, mask)
 
     def barrier():
         if world > 1:
@@ -338,13 +349,13 @@ def main():
 
     # ---------------- device-resident throughput ("value")
     for i in range(W):
-        eng.train_step(rays_b[i % n_b], projs_b[i % n_b], mask_b[i % n_b])
+        step(in_b[i % n_b], projs_b[i % n_b], mask_b[i % n_b])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
         j = (W + i) % n_b
-        loss = eng.train_step(rays_b[j], projs_b[j], mask_b[j])
+        loss = step(in_b[j], projs_b[j], mask_b[j])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -354,29 +365,30 @@ def main():
     # ---------------- end to end: pinned host inputs -> H2D -> step -> D2H of the loss, every step
     # (train_step copies the pinned host tensors straight into the buffers its graph reads: 3 H2D copies + 1 graph launch)
     for i in range(3):
-        eng.train_step(rays_h[i], projs_h[i], mask_h[i]).item()
+        step(in_h[i], projs_h[i], mask_h[i]).item()
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(K):
         j = (W + i) % n_b
-        host_loss = eng.train_step(rays_h[j], projs_h[j], mask_h[j]).item()      # H2D of the inputs, D2H read of the step's result
+        host_loss = step(in_h[j], projs_h[j], mask_h[j]).item()      # H2D of the inputs, D2H read of the step's result
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
-    h2d = rays_h[0].numel() * 4 + projs_h[0].numel() * 4 + mask_h[0].numel()
+    h2d = in_h[0].numel() * 4 + projs_h[0].numel() * 4 + mask_h[0].numel()
     d2h = 4
 
     # ---------------- per-kernel CUDA-event timing (instrumented eager pass, same workload)
     from neuralvolumetricreconstructionformedicalimages_b200.engine import EventTimer
     timer = EventTimer()
     for i in range(3):
-        eng.profiled_step(rays_b[i], projs_b[i], mask_b[i], None, EventTimer())
+        eng.profiled_step(None if use_pixels else in_b[i], projs_b[i], mask_b[i], None, EventTimer(), pixels=in_b[i] if use_pixels else None)
     torch.cuda.synchronize()
     for i in range(args.profile_steps):
-        eng.profiled_step(rays_b[i % n_b], projs_b[i % n_b], mask_b[i % n_b], None, timer)
+        j = i % n_b
+        eng.profiled_step(None if use_pixels else in_b[j], projs_b[j], mask_b[j], None, timer, pixels=in_b[j] if use_pixels else None)
     torch.cuda.synchronize()
     prof = timer.summary()
 
@@ -424,6 +436,8 @@ def main():
                            "peer": "one fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory",
                            "nccl": "NCCL all-reduce of the flat gradient + dense Adam", "local": "none (single GPU), dense Adam"}[eng.exchange_mode] + ")",
                        "per_gpu_batch": f"{N_RAYS}x{N_SAMPLES}", "cuda_graph": True,
+                       "ray_source": "detector pixels, rays generated in-kernel" if use_pixels else "rays tensor [N,8]",
+                       "sampler_uniforms": "in-kernel counter-based generator (no [N,S] buffer)",
                        "l2": "no explicit flush: every step streams 456 MB (dense Adam over 4 x 57 MB vectors) through the 126 MB L2; "
                              "each step uses a different ray batch"},
             "clocks": clocks,

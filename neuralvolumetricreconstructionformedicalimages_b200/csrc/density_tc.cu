@@ -112,10 +112,11 @@ __device__ __forceinline__ void gather_half(const GridParams &gp, const float (&
 // backward pass pays for.  The choice is made per warp and level from the number of runs (ballot).
 constexpr int AGG_LEVELS = 8;      // levels 0 .. AGG_LEVELS-1 may be aggregated
 constexpr int AGG_MAX_RUNS = 20;   // aggregate when the warp has at most this many runs
+// (both can be overridden for experiments through NAFB_DEBUG_SKIP: bits 8-13 = levels + 1, bits 16-21 = runs + 1)
 
 template <int C>
 __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, const int l, const float x0, const float x1, const float x2,
-                                         const uint32_t taddr, const bool valid, const bool try_agg, float *__restrict__ grad_table) {
+                                         const uint32_t taddr, const bool valid, const int agg_max_runs, float *__restrict__ grad_table) {
     const unsigned lane = threadIdx.x & 31u;
     float ge[C];
     umma::tmem_ldn<C>(taddr, ge);
@@ -129,13 +130,13 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
     locate(x2, lp.scale, g[2], f[2]);
     const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
     umma::tmem_wait_ld();
-    if (try_agg) {
+    if (agg_max_runs > 0) {
         // runs of equal cells among consecutive lanes (invalid lanes: a run of their own, never issued)
         const uint32_t k0 = valid ? (g[0] | (g[1] << 16)) : 0xffffffffu, k1 = valid ? g[2] : 0xffffffffu;
         const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
         const bool head = lane == 0 || p0 != k0 || p1 != k1;
         const uint32_t heads = __ballot_sync(0xffffffffu, head);
-        if (__popc(heads) <= AGG_MAX_RUNS) {
+        if (__popc(heads) <= agg_max_runs) {
             float v[8][C];
 #pragma unroll
             for (uint32_t idx = 0; idx < 8; ++idx) {
@@ -146,8 +147,10 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
                 for (int c = 0; c < C; ++c) v[idx][c] = valid ? __fmul_rn(w, ge[c]) : 0.f;
             }
             const uint32_t above = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));  // bit j: lane+1+j starts a new run
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
+            // only as many doubling steps as the longest run of the warp needs
+            const uint32_t my_len = head ? (above ? (uint32_t)__ffs(above) : 32u - lane) : 0u;
+            const uint32_t max_len = __reduce_max_sync(0xffffffffu, my_len);
+            for (uint32_t o = 1; o < max_len; o <<= 1) {
                 const bool same = (lane + o < 32) && ((above & ((1u << o) - 1u)) == 0u);
 #pragma unroll
                 for (uint32_t idx = 0; idx < 8; ++idx)
@@ -634,12 +637,13 @@ __global__ void __launch_bounds__(NT_B, 2) k_density_bwd_tc(const GridParams gp,
     bool valid_prev = false, have_prev = false;
     uint32_t tdenc_prev = 0;      // TMEM address (lane base included) of the previous tile's d(encoding)
     const bool do_scatter = grad_table != nullptr && !(dbg & 1);
-    const bool agg_on = !(dbg & 16);
+    const int agg_levels = (dbg & 16) ? 0 : (((dbg >> 8) & 63) ? ((dbg >> 8) & 63) - 1 : AGG_LEVELS);
+    const int agg_runs = ((dbg >> 16) & 63) ? ((dbg >> 16) & 63) - 1 : AGG_MAX_RUNS;
     auto scatter_slot = [&](const int slot) {   // 8 slots cover the NLH levels of the thread
         if (!have_prev) return;
         for (int li = slot * NLH / 8; li < (slot + 1) * NLH / 8; ++li) {
             const int l = 2 * li + half;
-            scatter_one<C>(lvs, l, xp[0], xp[1], xp[2], tdenc_prev + (uint32_t)(l * C), valid_prev, agg_on && l < AGG_LEVELS, grad_table);
+            scatter_one<C>(lvs, l, xp[0], xp[1], xp[2], tdenc_prev + (uint32_t)(l * C), valid_prev, l < agg_levels ? agg_runs : 0, grad_table);
         }
     };
 

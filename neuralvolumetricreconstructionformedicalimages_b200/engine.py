@@ -345,14 +345,14 @@ class NAFEngine:
             return s["t_rand"]
         return None
 
-    def profiled_step(self, rays, projs, mask, t_rand, timer):
+    def profiled_step(self, rays, projs, mask, t_rand, timer, pixels=None):
         """Same work as train_step, launched eagerly (no graph) with a CUDA-event pair around every kernel."""
-        N = rays.shape[0]
+        N = pixels.shape[0] if pixels is not None else rays.shape[0]
         s = self._get_static(N, mask is not None)
         with torch.cuda.device(self.device):
-            tr = self._load_inputs(s, rays, projs, mask, t_rand)
+            tr = self._load_inputs(s, rays, projs, mask, t_rand, pixels)
             par = self._parity()
-            self._whole_step(s, par, timer, tr)
+            self._whole_step(s, par, timer, tr, use_pixels=pixels is not None)
             self.step_count += 1
         return s["loss"][0]
 

@@ -6,7 +6,7 @@ import bench
 from neuralvolumetricreconstructionformedicalimages_b200 import fused
 dev = torch.device("cuda", 0)
 eng = bench.build_engine(dev)
-rays_b, projs_b, mask_b, geo = bench.synthetic_batches(4, dev, 1)
+_, rays_b, projs_b, mask_b, _ = bench.synthetic_batches(4, dev, 1)
 eng.use_cuda_graph = False
 for i in range(3):
     eng.train_step(rays_b[i], projs_b[i], mask_b[i])
