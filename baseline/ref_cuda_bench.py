@@ -9,11 +9,9 @@ Runs the reference's render / DensityNetwork / HashEncoder / calc_mse_loss + tor
   one_call  : one render() call per step (best case for the reference)
 Prints one JSON line per variant.  None of this repository's kernels are on that path.
 """
-import importlib.util
 import json
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -23,35 +21,12 @@ ROOT = os.path.dirname(HERE)
 REF = os.path.join(HERE, "_ref")
 
 
-def import_reference():
-    if not os.path.isdir(os.path.join(REF, "src")):
-        raise SystemExit("baseline/_ref/src is missing: run baseline/stage_ref.sh where /root/reference is mounted")
-    for name in ["matplotlib", "matplotlib.pyplot", "open3d", "skimage", "skimage.metrics", "imageio", "imageio.v2"]:
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["skimage.metrics"].structural_similarity = lambda *a, **k: 0.0
-    # the staged copy's JIT loader -> the pre-built extension
-    so = [f for f in os.listdir(os.path.join(REF, "build")) if f.endswith(".so")]
-    if not so:
-        raise SystemExit("baseline/_ref/build has no pre-built _hash_encoder .so")
-    spec = importlib.util.spec_from_file_location("_hash_encoder", os.path.join(REF, "build", so[0]))
-    ext = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(ext)
-    backend = types.ModuleType("src.encoder.hashencoder.backend")
-    backend._backend = ext
-    sys.path.insert(0, REF)
-    sys.modules["src.encoder.hashencoder.backend"] = backend
-    from src.encoder import get_encoder
-    from src.loss import calc_mse_loss
-    from src.network import get_network
-    from src.render import render
-    return get_encoder, get_network, render, calc_mse_loss
-
-
 def main():
     steps = int(os.environ.get("REF_STEPS", "30"))
     warmup = int(os.environ.get("REF_WARMUP", "5"))
-    get_encoder, get_network, render, calc_mse_loss = import_reference()
     sys.path.insert(0, ROOT)
+    from baseline.ref_loader import import_reference
+    get_encoder, get_network, render, calc_mse_loss = import_reference("cuda")
     import bench
     dev = torch.device("cuda", 0)
     _, rays_b, projs_b, mask_b, _ = bench.synthetic_batches(steps + warmup, dev, seed=1234)
