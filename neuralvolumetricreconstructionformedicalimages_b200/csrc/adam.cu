@@ -22,13 +22,19 @@ __global__ void __launch_bounds__(256) k_adam(float *__restrict__ param, float *
     float4 *g4 = reinterpret_cast<float4 *>(grad);
     float4 *m4 = reinterpret_cast<float4 *>(m_);
     float4 *v4 = reinterpret_cast<float4 *>(v_);
+    // L2 residency: the parameters are what the next forward pass gathers from (and the zeroed gradient what the next backward
+    // pass reduces into) -> evict-last; exp_avg / exp_avg_sq are touched once per step -> evict-first, so that the 228 MB they
+    // move do not flush the other 114 MB out of the 126 MB L2.
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
-        float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+        float4 p = ld_l2hint(p4 + i, keep), g = g4[i], m = ld_l2hint(m4 + i, stream), v = ld_l2hint(v4 + i, stream);
         adam_one(p.x, g.x, m.x, v.x, c);
         adam_one(p.y, g.y, m.y, v.y, c);
         adam_one(p.z, g.z, m.z, v.z, c);
         adam_one(p.w, g.w, m.w, v.w, c);
-        p4[i] = p; m4[i] = m; v4[i] = v;
+        st_l2hint(p4 + i, p, keep);
+        st_l2hint(m4 + i, m, stream);
+        st_l2hint(v4 + i, v, stream);
         if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // tail (n % 4)
@@ -54,13 +60,16 @@ __global__ void __launch_bounds__(256) k_adam_dev(float *__restrict__ param, flo
     float4 *g4 = reinterpret_cast<float4 *>(grad);
     float4 *m4 = reinterpret_cast<float4 *>(m_);
     float4 *v4 = reinterpret_cast<float4 *>(v_);
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();   // see k_adam
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
-        float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+        float4 p = ld_l2hint(p4 + i, keep), g = g4[i], m = ld_l2hint(m4 + i, stream), v = ld_l2hint(v4 + i, stream);
         adam_one(p.x, g.x, m.x, v.x, c);
         adam_one(p.y, g.y, m.y, v.y, c);
         adam_one(p.z, g.z, m.z, v.z, c);
         adam_one(p.w, g.w, m.w, v.w, c);
-        p4[i] = p; m4[i] = m; v4[i] = v;
+        st_l2hint(p4 + i, p, keep);
+        st_l2hint(m4 + i, m, stream);
+        st_l2hint(v4 + i, v, stream);
         if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // last block out increments the step (every block has read it by then)

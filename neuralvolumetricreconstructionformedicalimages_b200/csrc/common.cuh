@@ -177,6 +177,26 @@ __device__ __forceinline__ void red_add_entry_pair(float *tab, uint32_t par, uin
     red_add_entry<C>(tab, e1, v1);
 }
 
+// ---- L2 residency hints (createpolicy + ld/st .L2::cache_hint): what the next kernel gathers from stays, streams go first
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_l2hint(const float4 *a, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_l2hint(float4 *a, const float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ float leaky_relu(float x) { return x > 0.f ? x : 0.01f * x; }
 
 __device__ __forceinline__ float head_activation(float x, uint32_t head) {
