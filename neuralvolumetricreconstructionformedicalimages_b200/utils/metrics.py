@@ -1,0 +1,59 @@
+"""Evaluation metrics of the reference (src/utils/util.py:18-139), computed where the data lives (torch ops on the
+tensors' own device, float64 like the reference's numpy code) -- no device->host copy of the volume, no skimage.
+
+get_ssim_3d restates what the reference obtains from ``skimage.metrics.structural_similarity`` on a 3-D array without a
+channel axis (util.py:87-139): the N-dimensional SSIM of Wang et al. with a uniform 7x7x7 window, K1 = 0.01, K2 = 0.03,
+sample covariance (normalised by NP/(NP-1)), averaged over the interior (borders of (win-1)/2 cropped).  The reference
+averages three axis permutations of the same isotropic computation, i.e. the same number three times.  ``data_range``:
+the reference passes none, so skimage 0.19 (the version contemporary with its torch 1.11 stack) takes the dtype range of
+float images, 2.0; newer versions demand an explicit value -- it is a parameter here (default 2.0).
+skimage is not installed in this image, so this restatement is checked against an independent scipy evaluation
+(the test suite's CPU checker), not against skimage itself ("parity unpinned" for this one metric).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def get_mse(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """util.py:18-26 (complex inputs: squared magnitude of the difference)."""
+    if torch.is_complex(x) and torch.is_complex(y):
+        return torch.mean((x.real - y.real) ** 2 + (x.imag - y.imag) ** 2)
+    return torch.mean((x - y) ** 2)
+
+
+def get_psnr(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """util.py:29-51: PSNR of the min-max normalised magnitudes."""
+    x, y = torch.abs(x), torch.abs(y)
+    if torch.max(x) == 0 or torch.max(y) == 0:
+        return torch.zeros(1, device=x.device)
+    xn = (x - torch.min(x)) / (torch.max(x) - torch.min(x))
+    yn = (y - torch.min(y)) / (torch.max(y) - torch.min(y))
+    return -10.0 * torch.log10(get_mse(xn, yn))
+
+
+def get_psnr_3d(arr1: torch.Tensor, arr2: torch.Tensor, PIXEL_MAX: float = 1.0) -> float:
+    """util.py:55-84 for one volume: 20 log10(PIXEL_MAX / sqrt(mse)) in float64; 100 when the volumes are identical."""
+    a, b = arr1.detach().to(torch.float64), arr2.detach().to(torch.float64)
+    mse = torch.mean((a - b) ** 2)
+    if float(mse) == 0.0:
+        return 100.0
+    return float(20.0 * torch.log10(PIXEL_MAX / torch.sqrt(mse)))
+
+
+def get_ssim_3d(arr1: torch.Tensor, arr2: torch.Tensor, data_range: float = 2.0, win_size: int = 7) -> float:
+    """util.py:87-139 for one [D,H,W] volume (see the module docstring)."""
+    a = arr1.detach().to(torch.float64)[None, None]
+    b = arr2.detach().to(torch.float64)[None, None]
+    if min(a.shape[2:]) < win_size:
+        raise ValueError("win_size exceeds image extent")
+    NP = win_size ** 3
+    cov_norm = NP / (NP - 1.0)
+    pool = lambda t: F.avg_pool3d(t, win_size, stride=1)      # uniform filter restricted to the interior == filter + crop
+    ux, uy = pool(a), pool(b)
+    uxx, uyy, uxy = pool(a * a), pool(b * b), pool(a * b)
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2))
+    return float(S.mean())

@@ -308,3 +308,22 @@ def train_step(net, optimizer, rays, projs, n_samples, perturb, mask=None, chunk
     loss.backward()
     optimizer.step()
     return loss.detach()
+
+
+def ssim_3d(a, b, data_range=2.0, win_size=7) -> float:
+    """N-dimensional SSIM as skimage.metrics.structural_similarity evaluates it for a 3-D array without channel axis
+    (what util.py:87-139 averages three times): scipy uniform_filter (mode 'reflect'), sample covariance, K1 .01, K2 .03,
+    mean over the interior.  skimage itself is absent from this image; this is an independent scipy evaluation."""
+    from scipy.ndimage import uniform_filter
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    NP = win_size ** a.ndim
+    cov_norm = NP / (NP - 1.0)
+    f = lambda t: uniform_filter(t, size=win_size, mode="reflect")
+    ux, uy = f(a), f(b)
+    uxx, uyy, uxy = f(a * a), f(b * b), f(a * b)
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+    pad = (win_size - 1) // 2
+    return float(S[pad:-pad, pad:-pad, pad:-pad].mean())

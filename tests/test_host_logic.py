@@ -166,3 +166,24 @@ def test_pose_table_and_detector_fields(golden):
     assert np.array_equal(T[:, :9].reshape(-1, 3, 3), ref[:, :3, :3]) and np.array_equal(T[:, 9:], ref[:, :3, 3])
     d = G.detector_fields(geo)
     assert d["det_w"] == 10 and d["det_h"] == 6 and d["det_parallel"] == 1 and d["det_du"] == float(np.float32(0.0015))
+
+
+def test_metrics_match_reference_fixtures_and_oracle(golden):
+    """utils.metrics against the reference's get_psnr_3d output (fixture) and the scipy SSIM restatement of the oracle."""
+    from neuralvolumetricreconstructionformedicalimages_b200.utils import get_mse, get_psnr, get_psnr_3d, get_ssim_3d
+    from oracle import naf
+    fx = golden("geometry.npz")
+    a, b = torch.from_numpy(fx["psnr_a"]), torch.from_numpy(fx["psnr_b"])
+    assert abs(get_psnr_3d(a, b) - float(fx["psnr_3d"])) < 1e-9
+    assert get_psnr_3d(a, a) == 100.0
+    rng = np.random.default_rng(3)
+    v1 = rng.uniform(0, 1, (20, 17, 23)).astype(np.float32)
+    v2 = np.clip(v1 + rng.normal(0, 0.05, v1.shape), 0, 1).astype(np.float32)
+    s_ours, s_ref = get_ssim_3d(torch.from_numpy(v1), torch.from_numpy(v2)), naf.ssim_3d(v1, v2)
+    assert abs(s_ours - s_ref) < 1e-12 and 0.5 < s_ours < 1.0
+    assert abs(get_ssim_3d(torch.from_numpy(v1), torch.from_numpy(v1)) - 1.0) < 1e-12
+    x = torch.from_numpy(rng.uniform(0, 1, (5, 6)).astype(np.float32))
+    y = torch.from_numpy(rng.uniform(0, 1, (5, 6)).astype(np.float32))
+    assert abs(float(get_mse(x, y)) - float(((x - y) ** 2).mean())) < 1e-12 and float(get_psnr(x, y)) > 0
+    z = torch.complex(x, y)
+    assert abs(float(get_mse(z, z * 0)) - float((x ** 2 + y ** 2).mean())) < 1e-6
