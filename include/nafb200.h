@@ -255,7 +255,10 @@ int nafb_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg
 
 /* Arithmetic of the fused density kernels: 0 (default) = tcgen05 tensor cores with bf16x3 split
  * operands and fp32 TMEM accumulation wherever the configuration allows (4 x 32 MLP, skip at 2),
- * 1 = fp32 SIMT FMAs everywhere (bit-reproducible dot-product order; the general-shape path). */
+ * 1 = fp32 SIMT FMAs everywhere (bit-reproducible dot-product order; the general-shape path),
+ * 2 = as 0 with the warp-specialised forward kernel (producer warps gather the next tile while the
+ *     epilogue warps run the MLP chain of the current one; measured slower than 0 at chest_50, kept
+ *     selectable: see DESIGN.md section 4.2). */
 int nafb_set_mlp_mode(int mode);
 
 /* ------------------------------------------------------------------ diagnostics

@@ -16,6 +16,8 @@
 // Scope of this edition: in_dim (L*C) == 32, hidden == 32, out_dim == 1, any number of layers
 // up to NAFB_MAX_LAYERS, skips anywhere in [1, n_layers-2] -- i.e. every shipped config
 // (config/*.yaml: 16x2 hash grid, 4x32 MLP, skips [2]).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sampler.cuh"
 
@@ -28,6 +30,8 @@ int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerPa
 int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
                        float *grad_table, float *partials, const void *stash, long long *stamps, int grid, cudaStream_t s);
 int nafb_tc_bwd_grid(uint64_t n_tiles);
+int nafb_launch_fwd_ws(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
+                       float *pts, int32_t *flags, void *stash, cudaStream_t s);
 static int g_mlp_mode = 0;  // 0: tensor cores when the configuration allows, 1: fp32 SIMT everywhere
 
 namespace {
@@ -592,7 +596,7 @@ int launch_bwd(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp
 extern "C" {
 
 uint64_t nafb_density_stash_bytes(const nafb_grid *grid, const nafb_mlp *mlp, uint64_t n_points) {
-    if (!grid || !mlp || g_mlp_mode != 0 || !nafb_tc_config_ok(grid, mlp)) return 0;
+    if (!grid || !mlp || g_mlp_mode == 1 || !nafb_tc_config_ok(grid, mlp)) return 0;
     return nafb_tc_stash_bytes(n_points);
 }
 
@@ -608,14 +612,15 @@ int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_
     if (P == 0) return NAFB_OK;
     if (src != NAFB_SRC_RAYS && (acc || z_vals || pts_out)) NAFB_FAIL(NAFB_ERR_INVALID, "density_forward: acc/z_vals/pts_out need the RAYS source");
     cudaStream_t s = (cudaStream_t)stream;
-    if (g_mlp_mode == 0 && nafb_tc_config_ok(grid, mlp)) return nafb_launch_fwd_tc(gp, *mlp, sp, src, P, sigma, acc, z_vals, pts_out, flags, stash, s);
+    if (g_mlp_mode != 1 && nafb_tc_config_ok(grid, mlp))   // mode 2: warp-specialised forward (producer / MMA / epilogue warps)
+        return (g_mlp_mode == 2 ? nafb_launch_fwd_ws : nafb_launch_fwd_tc)(gp, *mlp, sp, src, P, sigma, acc, z_vals, pts_out, flags, stash, s);
 #define CALL(S_, C_) launch_fwd<S_, C_>(gp, *mlp, sp, P, sigma, acc, z_vals, pts_out, flags, s)
     DISPATCH_SRC_C(src, gp.C, CALL);
 #undef CALL
 }
 
 int nafb_set_mlp_mode(int mode) {
-    if (mode != 0 && mode != 1) NAFB_FAIL(NAFB_ERR_INVALID, "set_mlp_mode: mode must be 0 (tensor cores) or 1 (fp32 SIMT)");
+    if (mode < 0 || mode > 2) NAFB_FAIL(NAFB_ERR_INVALID, "set_mlp_mode: mode must be 0 (tensor cores), 1 (fp32 SIMT) or 2 (tensor cores, warp-specialised forward)");
     g_mlp_mode = mode;
     return NAFB_OK;
 }

@@ -88,6 +88,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
         : "memory");
 }
 
+// long waits (a consumer role waiting for a producer role): back off between polls so that the polling warps do not
+// compete with the working warps for issue slots and the shared-memory pipe
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *mbar, uint32_t parity, unsigned ns = 64) {
+    const uint32_t a = smem_u32(mbar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(ns);
+    }
+}
+
 // ---- named barriers (producer / consumer hand-off between warp roles): `threads` = arriving + syncing threads
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");

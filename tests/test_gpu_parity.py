@@ -33,7 +33,7 @@ DEV = "cuda"
 
 # Arithmetic of the fused density kernels: 0 = tcgen05 tensor cores (bf16x3 split operands, fp32 accumulation
 # in TMEM; the default), 1 = fp32 SIMT FMAs.  Every density / render / engine test runs in both modes.
-both_modes = pytest.mark.parametrize("mlp_mode", [0, 1], ids=["tcgen05", "simt"], indirect=True)
+both_modes = pytest.mark.parametrize("mlp_mode", [0, 1, 2], ids=["tcgen05", "simt", "tcgen05-ws"], indirect=True)
 
 
 @pytest.fixture
