@@ -26,6 +26,9 @@ namespace {
 
 constexpr int TILE = 128;
 constexpr int NT = 256;
+#ifndef FWD_CTAS
+#define FWD_CTAS 3   // forward CTAs per SM (measured at chest_50: 2 -> 93 us, 3 -> 83 us, 4 -> 125 us: the L1 left over by 4 x 50 KB of shared memory is too small for the coarse levels)
+#endif
 constexpr int NT_B = 288;  // backward: 8 epilogue warps + 1 MMA-issue warp
 constexpr uint32_t LBO = 128;  // bytes between adjacent 8-column chunks of a row group
 
@@ -346,7 +349,7 @@ constexpr uint32_t FX_SBO = 1024, FX_HALF = 16384;
 constexpr uint32_t FWD_SMEM = 2 * FX_HALF + 2 * W_HALF + sizeof(SmallParams) + sizeof(TileCtl) + TILE * sizeof(float) + 128;
 
 template <int SRC, int C>
-__global__ void __launch_bounds__(NT, 3) k_density_fwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
+__global__ void __launch_bounds__(NT, FWD_CTAS) k_density_fwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           float *__restrict__ sigma, float *__restrict__ acc_out, float *__restrict__ z_out,
                                                           float *__restrict__ pts_out, int32_t *__restrict__ flags, uint8_t *__restrict__ stash,
                                                           const int dbg) {
@@ -869,7 +872,7 @@ int launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams 
         configured = true;
     }
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
-    const uint64_t cap = (uint64_t)nafb_sm_count() * 3;
+    const uint64_t cap = (uint64_t)nafb_sm_count() * FWD_CTAS;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
     k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags, stash, nafb_debug_flags());
     NAFB_CHECK_LAUNCH("density_forward(tc)");
