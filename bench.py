@@ -314,7 +314,7 @@ def extra_workloads(device, world, rank):
     rays_all = G.rays_with_near_far(data["angles"][:16], geo, device)
     eng = make_engine(384, None)
     rb, pb, mb = batches(rays_all, 65536, 3)
-    ms, loss = _time_steps(eng, rb, pb, mb, 4, 2, world)
+    ms, loss = _time_steps(eng, rb, pb, mb, 4, 4, world)    # 4 warm-up steps: eager + graph capture for both gradient parities
     pts = 65536 * 384
     out["large_batch"] = {"workload": "65536 rays x 384 samples per step per GPU, 256^3 volume, cone beam, one MSE chunk", "ms_per_step": ms,
                           "value": world * pts / (ms * 1e-3), "unit": "samples/s", "loss": loss,
@@ -375,9 +375,19 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("NAFB_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its banner on stdout, which must carry exactly one JSON line
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout when the first communicator is created; stdout must carry exactly one
+        # JSON line, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     K, W = args.steps, args.warmup
 
     eng = build_engine(device)
