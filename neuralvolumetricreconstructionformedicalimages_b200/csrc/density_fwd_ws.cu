@@ -7,10 +7,13 @@
 //
 //   warps 0-7   epilogue ("chain") warps: thread (r, half) = TMEM lane r, 16 of the 32 feature columns.  TMEM -> bias,
 //               LeakyReLU -> bf16 (hi, lo) operand of the next layer; head, ray integral.
-//   warps 8-11  producers: thread g generates sample point g of the NEXT tile (ray generation, stratified sampling,
-//               clamp, normalisation -- sampler.cuh, bit-exact), gathers its 16 levels x 8 corners, writes the encoding
-//               as bf16 (hi, lo) straight into the operand buffer (double buffered) and into the stash for backward.
-//   warp 12     one lane issues every tcgen05.mma of the CTA.
+//   warps 8-23  producers: thread (g, q) generates sample point g of the NEXT tile (ray generation, stratified
+//               sampling, clamp, normalisation -- sampler.cuh, bit-exact), gathers quarter q of its levels (one 16-byte
+//               operand chunk = 8 columns; loads of two levels in flight), writes it as bf16 (hi, lo) straight into the
+//               operand buffer (double buffered) and into the stash for backward.
+//   warp 24     one lane issues every tcgen05.mma of the CTA.
+// One CTA per SM (800 threads): 512 gathering threads keep the L2 busy while a single chain runs (the chain of one tile is
+// ~2.7 us, the gather of one tile ~5 us at the measured L2 sector rate), and the L1 keeps 150+ KB for the coarse levels.
 //
 // Hand-off: mbarriers full[b] (128 producer arrivals) / empty[b] (256 epilogue arrivals) around the two encoding
 // buffers, one mbarrier for MMA completion (tcgen05.commit), named barrier 1 for "operands of the next layer written".
@@ -23,7 +26,8 @@ int nafb_debug_flags();
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NT_WS = 416;          // 8 epilogue warps + 4 producer warps + 1 MMA warp
+constexpr int NT_WS = 800;          // 8 epilogue warps + 16 producer warps + 1 MMA warp
+constexpr int MMA_WARP = 24;
 constexpr uint32_t LBO = 128;
 constexpr uint32_t E_SBO = 512, E_IMG = 8192;    // one encoding image (hi or lo): 128 rows x 4 chunks
 constexpr uint32_t H_SBO = 512, H_IMG = 8192;    // hidden activations, same shape
@@ -71,13 +75,14 @@ __device__ __forceinline__ void load_weight_images(const nafb_mlp &mp, uint8_t *
     }
 }
 
-// 8 consecutive encoding columns (one 16-byte operand chunk) of one point
+// 8 consecutive encoding columns (operand chunk `chunk`: levels chunk*LPC .. chunk*LPC+LPC-1) of one point; the loads of
+// level li+1 are issued before level li is consumed
 template <int C>
-__device__ __forceinline__ void gather_chunk(const LevelParams *__restrict__ lvs, const float *__restrict__ table, const float (&x01)[3],
-                                             const int chunk, float (&enc8)[8]) {
-    constexpr int LPC = 8 / C;   // levels per chunk
-#pragma unroll
-    for (int li = 0; li < LPC; ++li) {
+__device__ __forceinline__ void gather_chunk_ws(const LevelParams *__restrict__ lvs, const float *__restrict__ table, const float (&x01)[3],
+                                                const int chunk, float (&enc8)[8]) {
+    constexpr int LPC = 8 / C;
+    float v[LPC][8][C];
+    auto issue = [&](const int li) {
         const LevelParams lp = lvs[chunk * LPC + li];
         const float *__restrict__ tab = table + (size_t)lp.offset * C;
         uint32_t g[3];
@@ -86,10 +91,16 @@ __device__ __forceinline__ void gather_chunk(const LevelParams *__restrict__ lvs
         for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
         const uint32_t par = addr_parity8(tab);
         const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
-        float v[8][C];
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j)
-            load_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v[2 * j], v[2 * j + 1]);
+            load_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v[li][2 * j], v[li][2 * j + 1]);
+    };
+    auto consume = [&](const int li) {
+        const float scale = lvs[chunk * LPC + li].scale;
+        uint32_t g;
+        float f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) locate(x01[d], scale, g, f[d]);
         float res[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) res[c] = 0.f;
@@ -99,15 +110,21 @@ __device__ __forceinline__ void gather_chunk(const LevelParams *__restrict__ lvs
 #pragma unroll
             for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
 #pragma unroll
-            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[idx][c], res[c]);
+            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[li][idx][c], res[c]);
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) enc8[li * C + c] = res[c];
+    };
+    issue(0);
+#pragma unroll
+    for (int li = 0; li < LPC; ++li) {
+        if (li + 1 < LPC) issue(li + 1);
+        consume(li);
     }
 }
 
 template <int SRC, int C>
-__global__ void __launch_bounds__(NT_WS, 2) k_density_fwd_ws(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
+__global__ void __launch_bounds__(NT_WS, 1) k_density_fwd_ws(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                              float *__restrict__ sigma, float *__restrict__ acc_out, float *__restrict__ z_out,
                                                              float *__restrict__ pts_out, int32_t *__restrict__ flags, uint8_t *__restrict__ stash) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -124,8 +141,8 @@ __global__ void __launch_bounds__(NT_WS, 2) k_density_fwd_ws(const GridParams gp
     load_weight_images(mp, W_hi, W_lo, small);
     if (t < NAFB_MAX_LEVELS) lvs[t] = gp.lv[t];
     if (t == 0) {
-        umma::mbar_init(&ctl->full[0], TILE);
-        umma::mbar_init(&ctl->full[1], TILE);
+        umma::mbar_init(&ctl->full[0], 4 * TILE);
+        umma::mbar_init(&ctl->full[1], 4 * TILE);
         umma::mbar_init(&ctl->empty[0], 256);
         umma::mbar_init(&ctl->empty[1], 256);
         umma::mbar_init(&ctl->mma, 1);
@@ -139,9 +156,9 @@ __global__ void __launch_bounds__(NT_WS, 2) k_density_fwd_ws(const GridParams gp
     const uint32_t tmem = ctl->tmem_base;
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
 
-    if (warp >= 8 && warp < 12) {
+    if (warp >= 8 && warp < MMA_WARP) {
         // ============================================================ producers
-        const int g = t - 256;   // row of the tile
+        const int g = (t - 256) & 127, q = (t - 256) >> 7;   // row of the tile, which quarter of the levels (operand chunk)
         int bad = 0;
         uint32_t it = 0;
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -155,7 +172,7 @@ __global__ void __launch_bounds__(NT_WS, 2) k_density_fwd_ws(const GridParams gp
                 fetch_point<SRC>(sp, p, x);
                 if (!(x[0] >= -sp.bound && x[0] <= sp.bound && x[1] >= -sp.bound && x[1] <= sp.bound && x[2] >= -sp.bound && x[2] <= sp.bound))
                     bad |= 1;
-                if constexpr (SRC == NAFB_SRC_RAYS) {
+                if constexpr (SRC == NAFB_SRC_RAYS) if (q == 0) {
                     ray = (uint32_t)(p / sp.n_samples);
                     const uint32_t i = (uint32_t)(p - (uint64_t)ray * sp.n_samples);
                     if (pts_out) { pts_out[3 * p] = x[0]; pts_out[3 * p + 1] = x[1]; pts_out[3 * p + 2] = x[2]; }
@@ -173,13 +190,12 @@ __global__ void __launch_bounds__(NT_WS, 2) k_density_fwd_ws(const GridParams gp
             umma::mbar_wait_backoff(&ctl->empty[b], ((it >> 1) & 1u) ^ 1u);
             uint8_t *e_hi = E + b * 2 * E_IMG, *e_lo = e_hi + E_IMG;
             uint8_t *st = stash ? stash + tile * ST_TILE : nullptr;
-#pragma unroll
-            for (int chunk = 0; chunk < 4; ++chunk) {
+            {
                 float enc8[8];
-                gather_chunk<C>(lvs, gp.table, x01, chunk, enc8);
+                gather_chunk_ws<C>(lvs, gp.table, x01, q, enc8);
                 uint4 h, l;
                 umma::split_chunk(enc8, h, l);
-                const uint32_t off = umma::canon_off(g, chunk, LBO, E_SBO);
+                const uint32_t off = umma::canon_off(g, q, LBO, E_SBO);
                 *reinterpret_cast<uint4 *>(e_hi + off) = h;
                 *reinterpret_cast<uint4 *>(e_lo + off) = l;
                 if (st) {
@@ -187,13 +203,15 @@ __global__ void __launch_bounds__(NT_WS, 2) k_density_fwd_ws(const GridParams gp
                     *reinterpret_cast<uint4 *>(st + ST_HALF + off) = l;
                 }
             }
-            meta[b].dn[g] = dn;
-            meta[b].ray[g] = ray;
+            if (q == 0) {
+                meta[b].dn[g] = dn;
+                meta[b].ray[g] = ray;
+            }
             umma::fence_proxy_async();
             mbar_arrive(&ctl->full[b]);
         }
         if (flags && bad) atomicOr(flags, bad);
-    } else if (warp == 12) {
+    } else if (warp == MMA_WARP) {
         // ============================================================ MMA issue
         const uint32_t e0 = umma::smem_u32(E), h_hi = umma::smem_u32(H_hi), h_lo = umma::smem_u32(H_lo);
         const uint32_t w_hi = umma::smem_u32(W_hi), w_lo = umma::smem_u32(W_lo);
@@ -332,7 +350,7 @@ int launch_ws(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp,
         configured = true;
     }
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
-    const uint64_t cap = (uint64_t)nafb_sm_count() * 2;
+    const uint64_t cap = (uint64_t)nafb_sm_count();
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
     k_density_fwd_ws<SRC, C><<<grid, NT_WS, WS_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags, stash);
     NAFB_CHECK_LAUNCH("density_forward(ws)");
