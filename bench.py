@@ -511,7 +511,11 @@ def main():
             "metric": "train samples/sec (rays x samples / s)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (rays sharded, parameters replicated; exchange: " + {
-                           "peer": "one fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory",
+                           "push": "one fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (gradients pushed to their "
+                                   "owners, parameters pushed back: stores only)",
+                           "nvls": "one fused reduce-scatter + Adam + all-gather kernel over NVLink, gradients added in the NVSwitch "
+                                   "(multimem.ld_reduce) and parameters multicast (multimem.st)",
+                           "peer": "one fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (P2P loads / stores)",
                            "nccl": "NCCL all-reduce of the flat gradient + dense Adam", "local": "none (single GPU), dense Adam"}[eng.exchange_mode] + ")",
                        "per_gpu_batch": f"{N_RAYS}x{N_SAMPLES}", "cuda_graph": True,
                        "ray_source": "detector pixels, rays generated in-kernel" if use_pixels else "rays tensor [N,8]",

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 5
+#define NAFB_ABI_VERSION 7
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -223,6 +223,7 @@ int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
 #define NAFB_XFLAG_DONE 8     /* [8..15] written by rank i: "I have finished writing your parameters"          */
 #define NAFB_XFLAG_ERROR 16   /* != 0: a spin timed out (value - 1 = index of the flag that never arrived)     */
 #define NAFB_XFLAG_TICKET 17  /* local block counter                                                           */
+#define NAFB_XFLAG_TICKET2 18 /* local block counter of the push edition's second phase                        */
 #define NAFB_XFLAG_WORDS 32
 
 typedef struct nafb_exchange {
@@ -236,6 +237,18 @@ typedef struct nafb_exchange {
     uint32_t *state;                   /* optional device nafb_step_state: when non-NULL the epoch is state[0] + 1 and
                                           the learning rate state[3] (the `step` / `lr` arguments are ignored), and
                                           the kernel increments state[0]: the launch can sit in a replayed CUDA graph */
+    float *mc_param;                   /* optional NVLS (NVLink SHARP) multicast address of the parameter vector ...    */
+    const float *mc_grad;              /* ... and of this step's gradient: the slice sum is then one multimem.ld_reduce
+                                          per element (added inside the NVSwitch) and the new parameters one multimem.st
+                                          (multicast to every replica): ~ n*4 bytes per GPU and direction instead of
+                                          2*(W-1)/W * n*4.  Both NULL: plain P2P loads / stores.                        */
+    float *stage[NAFB_MAX_RANKS];      /* optional PUSH edition (all non-NULL): every rank's staging area, [W][stage_slot]
+                                          floats in peer memory.  Ranks then push their gradient slices into the owners'
+                                          staging areas and the owners push the parameters back: stores only over NVLink
+                                          (posted writes run faster than remote reads).  grad[rank] is then the ONE gradient
+                                          buffer of this rank (peers never read it; it leaves the kernel zeroed), grad_zero
+                                          and grad[w != rank] are ignored.                                              */
+    uint64_t stage_slot;               /* floats per staging slot, multiple of 4, >= the largest slice                  */
 } nafb_exchange;
 
 int nafb_peer_alloc(uint64_t bytes, void **ptr, unsigned char *handle64);

@@ -42,6 +42,11 @@ struct ExchangeParams {
     AdamConst c;           // host-evaluated constants (state == nullptr)
     uint32_t *state;       // device step state, or nullptr
     float beta1, beta2, eps, gscale;
+    float *mc_param;       // NVLS multicast addresses of the parameter vector / this parity's gradient, or nullptr
+    const float *mc_grad;
+    float *stage[MAXR];    // push mode: every rank's staging area [W][slot4 float4] (slot r of rank w: written by rank r)
+    float *grad_local;     // push mode: my (single) gradient buffer, cleared as it is consumed
+    uint64_t slot4;        // float4 per staging slot (>= the largest slice)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -60,6 +65,16 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // peer loads / stores: bypass L1 (the data lives in another GPU's memory and is never reused by this SM)
 __device__ __forceinline__ float4 ld_peer(const float4 *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_peer(float4 *p, const float4 v) { __stcg(p, v); }
+
+// NVLS (NVLink SHARP): one load returns the SUM over all replicas, reduced inside the NVSwitch; one store is multicast to all
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4 *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float4 *mc, const float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // wait until flag word `idx0 + w` of the LOCAL block is >= epoch for every rank w
 __device__ __forceinline__ void wait_all(const ExchangeParams &P, uint32_t idx0, uint32_t epoch) {
@@ -89,12 +104,16 @@ __global__ void __launch_bounds__(512) k_adam_exchange(const ExchangeParams P) {
     __syncthreads();
     const uint32_t epoch = s_epoch;
     const AdamConst c = s_c;
+    // debug time stamps (ns, %globaltimer) of block 0 in flag words 20..27: start, arrived, slice done, all done
+    unsigned long long *stamps = reinterpret_cast<unsigned long long *>(P.flags[P.rank] + 20);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
     // ---- 1. tell every rank (myself included) that my gradient is complete, then wait for everybody's
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
         st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_ARRIVE + P.rank, epoch);
     }
     wait_all(P, NAFB_XFLAG_ARRIVE, epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = globaltimer_ns();
 
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     // ---- 2. clear my gradient buffer of the other parity (its readers finished before they arrived at this epoch)
@@ -102,43 +121,75 @@ __global__ void __launch_bounds__(512) k_adam_exchange(const ExchangeParams P) {
         float4 *z = reinterpret_cast<float4 *>(P.grad_zero);
         for (uint64_t i = gid; i < P.n4; i += stride) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // ---- 3. my slice: sum of the W gradients (rank order), Adam, new parameters to all W replicas.
-    // U elements per thread and iteration keep U*W peer loads in flight (NVLink latency is a few microseconds).
-    constexpr int U = W == 2 ? 4 : (W == 4 ? 2 : 1);
-    float4 *m4 = reinterpret_cast<float4 *>(P.m), *v4 = reinterpret_cast<float4 *>(P.v);
-    const float4 *p_in = reinterpret_cast<const float4 *>(P.param[P.rank]);
-    for (uint64_t i0 = P.s0 + gid; i0 < P.s1; i0 += (uint64_t)U * stride) {
-        float4 g[U][MAXR], p[U], m[U], v[U];
+    if (P.mc_grad) {
+        // ---- 3 (NVLS). my slice: the switch adds the W gradients (multimem.ld_reduce), Adam, one multicast store updates all
+        // W replicas.  Per GPU and direction ~ n*4 bytes instead of 2*(W-1)/W * n*4.
+        float4 *m4 = reinterpret_cast<float4 *>(P.m), *v4 = reinterpret_cast<float4 *>(P.v);
+        const float4 *p_in = reinterpret_cast<const float4 *>(P.param[P.rank]);
+        const float4 *gmc = reinterpret_cast<const float4 *>(P.mc_grad);
+        float4 *pmc = reinterpret_cast<float4 *>(P.mc_param);
+        constexpr int UN = 4;
+        for (uint64_t i0 = P.s0 + gid; i0 < P.s1; i0 += (uint64_t)UN * stride) {
+            float4 s[UN], p[UN], m[UN], v[UN];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t i = i0 + (uint64_t)u * stride;
-            if (i < P.s1) {
+            for (int u = 0; u < UN; ++u) {
+                const uint64_t i = i0 + (uint64_t)u * stride;
+                if (i < P.s1) { s[u] = multimem_ld_reduce_add(gmc + i); p[u] = p_in[i]; m[u] = m4[i - P.s0]; v[u] = v4[i - P.s0]; }
+            }
 #pragma unroll
-                for (int w = 0; w < MAXR; ++w)
-                    if (w < (int)world) g[u][w] = ld_peer(reinterpret_cast<const float4 *>(P.grad[w]) + i);
-                p[u] = p_in[i]; m[u] = m4[i - P.s0]; v[u] = v4[i - P.s0];
+            for (int u = 0; u < UN; ++u) {
+                const uint64_t i = i0 + (uint64_t)u * stride;
+                if (i < P.s1) {
+                    adam_one(p[u].x, s[u].x, m[u].x, v[u].x, c);
+                    adam_one(p[u].y, s[u].y, m[u].y, v[u].y, c);
+                    adam_one(p[u].z, s[u].z, m[u].z, v[u].z, c);
+                    adam_one(p[u].w, s[u].w, m[u].w, v[u].w, c);
+                    m4[i - P.s0] = m[u];
+                    v4[i - P.s0] = v[u];
+                    multimem_st(pmc + i, p[u]);
+                }
             }
         }
+    } else {
+    // ---- 3. my slice: sum of the W gradients (rank order), Adam, new parameters to all W replicas.
+        // U elements per thread and iteration keep U*W peer loads in flight (NVLink latency is a few microseconds).
+        constexpr int U = W == 2 ? 4 : (W == 4 ? 2 : 1);
+        float4 *m4 = reinterpret_cast<float4 *>(P.m), *v4 = reinterpret_cast<float4 *>(P.v);
+        const float4 *p_in = reinterpret_cast<const float4 *>(P.param[P.rank]);
+        for (uint64_t i0 = P.s0 + gid; i0 < P.s1; i0 += (uint64_t)U * stride) {
+            float4 g[U][MAXR], p[U], m[U], v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t i = i0 + (uint64_t)u * stride;
-            if (i < P.s1) {
-                float4 s = g[u][0];
+            for (int u = 0; u < U; ++u) {
+                const uint64_t i = i0 + (uint64_t)u * stride;
+                if (i < P.s1) {
 #pragma unroll
-                for (int w = 1; w < MAXR; ++w)
-                    if (w < (int)world) { s.x += g[u][w].x; s.y += g[u][w].y; s.z += g[u][w].z; s.w += g[u][w].w; }
-                adam_one(p[u].x, s.x, m[u].x, v[u].x, c);
-                adam_one(p[u].y, s.y, m[u].y, v[u].y, c);
-                adam_one(p[u].z, s.z, m[u].z, v[u].z, c);
-                adam_one(p[u].w, s.w, m[u].w, v[u].w, c);
-                m4[i - P.s0] = m[u];
-                v4[i - P.s0] = v[u];
+                    for (int w = 0; w < MAXR; ++w)
+                        if (w < (int)world) g[u][w] = ld_peer(reinterpret_cast<const float4 *>(P.grad[w]) + i);
+                    p[u] = p_in[i]; m[u] = m4[i - P.s0]; v[u] = v4[i - P.s0];
+                }
+            }
 #pragma unroll
-                for (int w = 0; w < MAXR; ++w)
-                    if (w < (int)world) st_peer(reinterpret_cast<float4 *>(P.param[w]) + i, p[u]);
+            for (int u = 0; u < U; ++u) {
+                const uint64_t i = i0 + (uint64_t)u * stride;
+                if (i < P.s1) {
+                    float4 s = g[u][0];
+#pragma unroll
+                    for (int w = 1; w < MAXR; ++w)
+                        if (w < (int)world) { s.x += g[u][w].x; s.y += g[u][w].y; s.z += g[u][w].z; s.w += g[u][w].w; }
+                    adam_one(p[u].x, s.x, m[u].x, v[u].x, c);
+                    adam_one(p[u].y, s.y, m[u].y, v[u].y, c);
+                    adam_one(p[u].z, s.z, m[u].z, v[u].z, c);
+                    adam_one(p[u].w, s.w, m[u].w, v[u].w, c);
+                    m4[i - P.s0] = m[u];
+                    v4[i - P.s0] = v[u];
+#pragma unroll
+                    for (int w = 0; w < MAXR; ++w)
+                        if (w < (int)world) st_peer(reinterpret_cast<float4 *>(P.param[w]) + i, p[u]);
+                }
             }
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[2] = globaltimer_ns();
     // ---- 4. last block out: publish "done" to every rank, then wait until every rank is done with MY replica
     __threadfence_system();
     __syncthreads();
@@ -150,7 +201,108 @@ __global__ void __launch_bounds__(512) k_adam_exchange(const ExchangeParams P) {
     if (threadIdx.x == 0) P.flags[P.rank][NAFB_XFLAG_TICKET] = 0u;
     if (threadIdx.x < world) st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_DONE + P.rank, epoch);
     wait_all(P, NAFB_XFLAG_DONE, epoch);
+    if (threadIdx.x == 0) stamps[3] = globaltimer_ns();
     if (P.state && threadIdx.x == 0) P.state[NAFB_STATE_STEP] = epoch;   // every block has read the old value long ago
+}
+
+// ---------------------------------------------------------------------------------------------------- push edition
+// NVLink carries posted WRITES at a higher rate than it serves READS (measured here: the pull kernel's remote loads reach
+// ~450 GB/s, its remote stores drain at ~570 GB/s, and the two phases hardly overlap), so this edition moves every byte with
+// a store:
+//   phase 1  rank r copies slice w of ITS gradient into slot r of rank w's staging area (remote stores), for every w != r,
+//            clearing its gradient as it goes; when all of that is globally visible it raises pushed[r] on every rank;
+//   phase 2  once pushed[*] have arrived, rank w adds the W contributions of its slice in rank order (its own from the
+//            gradient buffer, the others from its local staging slots), applies Adam and stores the new parameters into
+//            all W replicas; done[w] as before.
+// pushed[r] doubles as "r no longer reads its parameters".  Peers never read a gradient buffer, so one gradient buffer per
+// rank suffices (no parity) and it leaves the kernel zeroed.  Every block waits for flags that other GPUs raise only after
+// ALL their blocks have run phase 1, so the grid must be fully resident (the launcher sizes it from the occupancy).
+__device__ __forceinline__ void slice_of(uint64_t n4, uint32_t w, uint32_t world, uint64_t &a, uint64_t &b) {
+    const uint64_t base = n4 / world, extra = n4 % world;
+    a = w * base + (w < extra ? w : extra);
+    b = a + base + (w < extra ? 1 : 0);
+}
+
+template <int W>
+__global__ void __launch_bounds__(512) k_adam_exchange_push(const ExchangeParams P) {
+    const uint32_t world = W > 0 ? (uint32_t)W : P.world;
+    __shared__ AdamConst s_c;
+    __shared__ uint32_t s_epoch, s_last;
+    if (threadIdx.x == 0) {
+        s_epoch = P.state ? P.state[NAFB_STATE_STEP] + 1u : P.epoch;
+        s_c = P.state ? adam_const_from_state(P.state, P.beta1, P.beta2, P.eps, P.gscale) : P.c;
+    }
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    const AdamConst c = s_c;
+    unsigned long long *stamps = reinterpret_cast<unsigned long long *>(P.flags[P.rank] + 20);   // debug: ns of block 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    float4 *g4 = reinterpret_cast<float4 *>(P.grad_local);
+
+    // ---- phase 1: push my contribution to every other owner, clearing what has been sent
+#pragma unroll 1
+    for (uint32_t k = 1; k < world; ++k) {
+        const uint32_t w = (P.rank + k) % world;          // start with my right neighbour: spreads the traffic over the links
+        uint64_t a, b;
+        slice_of(P.n4, w, world, a, b);
+        float4 *dst = reinterpret_cast<float4 *>(P.stage[w]) + (uint64_t)P.rank * P.slot4;
+        for (uint64_t i = a + gid; i < b; i += stride) {
+            const float4 v = g4[i];
+            st_peer(dst + (i - a), v);
+            g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(P.flags[P.rank] + NAFB_XFLAG_TICKET, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x == 0) P.flags[P.rank][NAFB_XFLAG_TICKET] = 0u;
+        if (threadIdx.x < world) st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_ARRIVE + P.rank, epoch);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = globaltimer_ns();
+    wait_all(P, NAFB_XFLAG_ARRIVE, epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[2] = globaltimer_ns();
+
+    // ---- phase 2: my slice
+    float4 *m4 = reinterpret_cast<float4 *>(P.m), *v4 = reinterpret_cast<float4 *>(P.v);
+    const float4 *p_in = reinterpret_cast<const float4 *>(P.param[P.rank]);
+    const float4 *st = reinterpret_cast<const float4 *>(P.stage[P.rank]);
+    for (uint64_t i = P.s0 + gid; i < P.s1; i += stride) {
+        float4 g[MAXR];
+#pragma unroll
+        for (int w = 0; w < MAXR; ++w)
+            if (w < (int)world) g[w] = (uint32_t)w == P.rank ? g4[i] : __ldcs(st + (uint64_t)w * P.slot4 + (i - P.s0));
+        float4 p = p_in[i], m = m4[i - P.s0], v = v4[i - P.s0];
+        float4 s = g[0];
+#pragma unroll
+        for (int w = 1; w < MAXR; ++w)
+            if (w < (int)world) { s.x += g[w].x; s.y += g[w].y; s.z += g[w].z; s.w += g[w].w; }
+        adam_one(p.x, s.x, m.x, v.x, c);
+        adam_one(p.y, s.y, m.y, v.y, c);
+        adam_one(p.z, s.z, m.z, v.z, c);
+        adam_one(p.w, s.w, m.w, v.w, c);
+        m4[i - P.s0] = m;
+        v4[i - P.s0] = v;
+        g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < MAXR; ++w)
+            if (w < (int)world) st_peer(reinterpret_cast<float4 *>(P.param[w]) + i, p);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[3] = globaltimer_ns();
+    // ---- last block out: "done" to every rank, then wait until every rank is done with MY replica and MY staging area
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(P.flags[P.rank] + NAFB_XFLAG_TICKET2, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x == 0) P.flags[P.rank][NAFB_XFLAG_TICKET2] = 0u;
+    if (threadIdx.x < world) st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_DONE + P.rank, epoch);
+    wait_all(P, NAFB_XFLAG_DONE, epoch);
+    if (P.state && threadIdx.x == 0) P.state[NAFB_STATE_STEP] = epoch;
 }
 
 }  // namespace
@@ -230,6 +382,20 @@ int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float
     P.n4 = x->n >> 2; P.s0 = i0 >> 2; P.s1 = i1 >> 2;
     P.c = make_adam_const((double)lr, beta1, beta2, eps, step ? step : 1u, grad_scale);
     P.state = x->state; P.beta1 = beta1; P.beta2 = beta2; P.eps = eps; P.gscale = grad_scale;
+    if ((x->mc_param != nullptr) != (x->mc_grad != nullptr)) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: mc_param and mc_grad go together");
+    if (((uintptr_t)x->mc_param | (uintptr_t)x->mc_grad) & 15) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: multicast addresses must be 16-byte aligned");
+    P.mc_param = x->mc_param; P.mc_grad = x->mc_grad;
+    const bool push = x->stage[x->rank] != nullptr;
+    if (push) {
+        for (uint32_t w = 0; w < x->world; ++w) {
+            if (!x->stage[w]) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: staging area of rank %u is null", w);
+            if ((uintptr_t)x->stage[w] & 15) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: staging areas must be 16-byte aligned");
+            P.stage[w] = x->stage[w];
+        }
+        P.grad_local = x->grad[x->rank];
+        P.slot4 = x->stage_slot >> 2;
+        if ((x->stage_slot & 3) || P.slot4 < (P.n4 + x->world - 1) / x->world) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: stage_slot too small");
+    }
     // persistent grid: as many blocks of 512 threads as are resident at once (blocks spin on the arrival flags)
     cudaStream_t s = (cudaStream_t)stream;
     auto launch = [&](auto kernel) {
@@ -237,11 +403,20 @@ int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 512, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
         kernel<<<(unsigned)(nafb_sm_count() * per_sm), 512, 0, s>>>(P);
     };
-    switch (x->world) {
-        case 2: launch(k_adam_exchange<2>); break;
-        case 4: launch(k_adam_exchange<4>); break;
-        case 8: launch(k_adam_exchange<8>); break;
-        default: launch(k_adam_exchange<0>); break;
+    if (push) {
+        switch (x->world) {
+            case 2: launch(k_adam_exchange_push<2>); break;
+            case 4: launch(k_adam_exchange_push<4>); break;
+            case 8: launch(k_adam_exchange_push<8>); break;
+            default: launch(k_adam_exchange_push<0>); break;
+        }
+    } else {
+        switch (x->world) {
+            case 2: launch(k_adam_exchange<2>); break;
+            case 4: launch(k_adam_exchange<4>); break;
+            case 8: launch(k_adam_exchange<8>); break;
+            default: launch(k_adam_exchange<0>); break;
+        }
     }
     NAFB_CHECK_LAUNCH("adam_exchange_step");
     return NAFB_OK;

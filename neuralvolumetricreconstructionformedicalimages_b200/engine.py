@@ -16,10 +16,12 @@ with the reference layout (encoder.embeddings, layers.i.weight/bias).
 Multi-GPU: one process per GPU, rays sharded across ranks, parameters replicated.  The step's one exchange
 (sum of the flat gradient over ranks -> Adam -> identical parameters everywhere) runs in one of two ways:
 
-  exchange="peer" (default when it can be set up): ONE kernel over NVLink peer memory (csrc/exchange.cu): every rank owns a
-      slice of the flat vector, pulls that slice of all ranks' gradients (P2P loads), applies Adam (optimizer state for the
-      slice only) and pushes the new parameters into all replicas (P2P stores).  Buffers come from nafb_peer_alloc and are
-      mapped into the peers with CUDA IPC; gradients are double buffered by step parity.
+  exchange="push" (default when it can be set up): ONE kernel over NVLink peer memory (csrc/exchange.cu): every rank owns a
+      slice of the flat vector; ranks push their gradient slices into the owners' staging areas, the owner adds them in rank
+      order, applies Adam (optimizer state for the slice only) and pushes the new parameters into all replicas -- stores
+      only over NVLink.  Buffers come from nafb_peer_alloc and are mapped into the peers with CUDA IPC.
+  exchange="peer": the pull edition (owners LOAD the peers' gradient slices; gradients double buffered by step parity);
+  exchange="nvls": as "peer" on torch symmetric memory, the sum done by the NVSwitch (multimem.ld_reduce / multimem.st).
   exchange="nccl": dist.all_reduce of the flat gradient, then the dense Adam kernel with grad_scale = 1/world.
 
 The voxel query shards by slabs of the outermost index and needs no collective.
@@ -84,38 +86,77 @@ class EventTimer:
 
 
 class PeerExchange:
-    """Peer-mapped flat buffers of all ranks + the descriptors of nafb_adam_exchange_step (one per gradient parity)."""
+    """Peer-mapped flat buffers of all ranks + the descriptors of nafb_adam_exchange_step (one per gradient parity).
+
+    Two ways to get memory every rank can address:
+      "nvls": torch symmetric memory (CUDA VMM + multicast object): peers' pointers AND one multicast address, so the kernel
+              can let the NVSwitch add the gradients (multimem.ld_reduce) and multicast the parameters (multimem.st);
+      "ipc" : cudaMalloc + CUDA IPC handles (nafb_peer_alloc / nafb_peer_open): plain P2P loads and stores (pull edition);
+      "push": same memory plus a staging area per rank: gradients are PUSHED to their owners and parameters pushed back --
+              stores only over NVLink, one gradient buffer per rank (the default: fastest measured).
+    """
 
     FLAG_BYTES = 256
 
-    def __init__(self, n, device, group, rank, world):
-        self.n, self.rank, self.world, self.device = int(n), rank, world, device
-        nbytes = self.FLAG_BYTES + 3 * self.n * 4
-        self.local = _lib.peer_alloc(nbytes)
-        handles = [None] * world
-        if world > 1:
-            dist.all_gather_object(handles, self.local.handle, group=group)
-        self.bufs = [self.local if w == rank else _lib.peer_open(handles[w], nbytes) for w in range(world)]
+    def __init__(self, n, device, group, rank, world, backend="ipc"):
+        self.n, self.rank, self.world, self.device, self.backend = int(n), rank, world, device, backend
         fb, seg = self.FLAG_BYTES, self.n * 4
-        self.flags = self.local.tensor(0, _lib.XFLAG_WORDS, torch.int32, device)
-        self.param = self.local.tensor(fb, self.n, torch.float32, device)
-        self.grad = [self.local.tensor(fb + (1 + k) * seg, self.n, torch.float32, device) for k in (0, 1)]
+        n_grad = 1 if backend == "push" else 2
+        slot = ((self.n // 4 + world - 1) // world) * 4 if backend == "push" else 0       # floats per staging slot
+        stage_off = fb + (1 + n_grad) * seg
+        nbytes = stage_off + world * slot * 4
+        mc_base = 0
+        if backend == "nvls":
+            import torch.distributed._symmetric_memory as symm_mem
+            self._symm = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
+            self._symm.zero_()
+            self._hdl = symm_mem.rendezvous(self._symm, group if group is not None else dist.group.WORLD)
+            mc_base = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+            if mc_base == 0:
+                raise RuntimeError("symmetric memory has no multicast (NVLS) address on this system")
+            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            self.bufs = []
+            flat = self._symm
+            self.flags = flat[: fb // 4].view(torch.int32)[: _lib.XFLAG_WORDS]
+            self.param = flat[fb // 4 : fb // 4 + self.n]
+            self.grad = [flat[fb // 4 + (1 + k) * self.n : fb // 4 + (2 + k) * self.n] for k in (0, 1)]
+            local_ptr = ptrs[rank]
+        else:
+            self.local = _lib.peer_alloc(nbytes)
+            handles = [None] * world
+            if world > 1:
+                dist.all_gather_object(handles, self.local.handle, group=group)
+            self.bufs = [self.local if w == rank else _lib.peer_open(handles[w], nbytes) for w in range(world)]
+            ptrs = [b.ptr for b in self.bufs]
+            self.flags = self.local.tensor(0, _lib.XFLAG_WORDS, torch.int32, device)
+            self.param = self.local.tensor(fb, self.n, torch.float32, device)
+            self.grad = [self.local.tensor(fb + (1 + k) * seg, self.n, torch.float32, device) for k in range(n_grad)]
+            local_ptr = self.local.ptr
         i0, i1 = _lib.exchange_slice(self.n, rank, world)
         self.slice = (i0, i1)
         self.exp_avg = torch.zeros(i1 - i0, device=device, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(i1 - i0, device=device, dtype=torch.float32)
         self.desc = []
-        for par in (0, 1):
+        for par in range(n_grad):
             x = _lib.Exchange()
             x.world, x.rank, x.n = world, rank, self.n
-            for w, b in enumerate(self.bufs):
-                x.flags[w] = b.ptr
-                x.param[w] = b.ptr + fb
-                x.grad[w] = b.ptr + fb + (1 + par) * seg
-            x.grad_zero = self.local.ptr + fb + (1 + (1 - par)) * seg
+            for w, base in enumerate(ptrs):
+                x.flags[w] = base
+                x.param[w] = base + fb
+                x.grad[w] = base + fb + (1 + par) * seg
+                if backend == "push":
+                    x.stage[w] = base + stage_off
+            if backend == "push":
+                x.stage_slot = slot
+            else:
+                x.grad_zero = local_ptr + fb + (1 + (1 - par)) * seg
             x.exp_avg, x.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+            if mc_base:
+                x.mc_param = mc_base + fb
+                x.mc_grad = mc_base + fb + (1 + par) * seg
             self.desc.append(x)
         if world > 1:
+            torch.cuda.synchronize(device)
             dist.barrier(group=group)   # every rank has mapped every buffer before anybody launches
 
     def step(self, par, lr, betas, eps, step, stream):
@@ -127,7 +168,7 @@ class PeerExchange:
 
     def close(self):
         for b in self.bufs:
-            if b is not self.local:
+            if b is not getattr(self, "local", None):
                 b.release()
 
 
@@ -151,8 +192,8 @@ class NAFEngine:
         self.use_stash = bool(use_stash)  # forward leaves the encodings (128 B/point) for backward instead of a second gather
         self.pg = process_group
         self.rank, self.world_size = parallel.world_info(process_group)
-        if exchange not in ("auto", "peer", "nccl"):
-            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        if exchange not in ("auto", "push", "nvls", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'push', 'peer', 'nvls' or 'nccl'")
         self.px = None
         self._flatten(exchange)
         if self.world_size > 1:   # replicas start identical
@@ -174,27 +215,33 @@ class NAFEngine:
             offs.append(n)
             n += _round_up(p.numel(), 4)
         n = _round_up(n, 4)
-        want_peer = exchange == "peer" or (exchange == "auto" and self.world_size > 1)
-        if want_peer:
+        # exchange over peer memory: NVLS (switch-side reduction + multicast) when the system offers it, else plain P2P over
+        # CUDA IPC, else NCCL.  Every rank must take the same decision, hence the all-reduce of the outcome.
+        candidates = {"auto": ["push"] if self.world_size > 1 else [], "push": ["push"], "nvls": ["nvls"], "peer": ["ipc"], "nccl": []}[exchange]
+        for backend in candidates:
             ok = 1
             try:
                 if self.world_size > _lib.NAFB_MAX_RANKS:
                     raise RuntimeError(f"peer exchange supports up to {_lib.NAFB_MAX_RANKS} ranks")
+                if backend == "nvls" and self.world_size == 1:
+                    raise RuntimeError("NVLS needs more than one rank")
                 with torch.cuda.device(self.device):
-                    self.px = PeerExchange(n, self.device, self.pg, self.rank, self.world_size)
-            except Exception as e:  # CUDA IPC unavailable (container / topology): every rank must take the same decision
-                if exchange == "peer" and self.world_size == 1:
+                    self.px = PeerExchange(n, self.device, self.pg, self.rank, self.world_size, backend)
+            except Exception as e:  # not available here (container / topology)
+                if self.world_size == 1:
                     raise
-                self._peer_error, ok, self.px = str(e), 0, None
+                self._peer_error, ok, self.px = f"{backend}: {e}", 0, None
             if self.world_size > 1:
                 t = torch.tensor([ok], device=self.device, dtype=torch.int32)
                 dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.pg)
                 if int(t.item()) == 0:
-                    if exchange == "peer":
-                        raise RuntimeError("peer exchange could not be set up on every rank: " + getattr(self, "_peer_error", "failed on a peer"))
                     if self.px is not None:
                         self.px.close()
                     self.px = None
+            if self.px is not None:
+                break
+        if self.px is None and exchange in ("push", "nvls", "peer"):
+            raise RuntimeError(f"exchange='{exchange}' could not be set up on every rank: " + getattr(self, "_peer_error", "failed on a peer"))
         if self.px is not None:
             self.flat_param = self.px.param
             self.flat_grads = self.px.grad                     # double buffered by step parity
@@ -222,11 +269,13 @@ class NAFEngine:
 
     @property
     def exchange_mode(self):
-        return "peer" if self.px is not None else ("nccl" if self.world_size > 1 else "local")
+        if self.px is not None:
+            return {"push": "push", "nvls": "nvls", "ipc": "peer"}[self.px.backend]
+        return "nccl" if self.world_size > 1 else "local"
 
     def _parity(self):
         """Which gradient buffer the coming step accumulates into (peer exchange: alternates; otherwise always 0)."""
-        return (self.step_count & 1) if self.px is not None else 0
+        return (self.step_count & 1) if (self.px is not None and len(self.flat_grads) == 2) else 0
 
     # ------------------------------------------------------------------ device-resident step state
     def _init_state(self, seed):

@@ -91,9 +91,9 @@ def test_engine_peer_mode_single_gpu_matches_default():
     dev = torch.device("cuda", 0)
     batches, S = _batches(0, 4)
     params = []
-    for mode in ("peer", "auto"):
-        eng = NAFEngine(_net(dev), lr=1e-3, n_samples=S, perturb=True, loss_chunk=100, use_cuda_graph=(mode == "peer"), exchange=mode)
-        assert eng.exchange_mode == ("peer" if mode == "peer" else "local")
+    for mode in ("peer", "push", "auto"):
+        eng = NAFEngine(_net(dev), lr=1e-3, n_samples=S, perturb=True, loss_chunk=100, use_cuda_graph=(mode != "auto"), exchange=mode)
+        assert eng.exchange_mode == (mode if mode != "auto" else "local")
         for rays, projs, t_rand in batches:
             loss = eng.train_step(rays.to(dev), projs.to(dev), None, t_rand.to(dev))
         torch.cuda.synchronize()
@@ -102,10 +102,11 @@ def test_engine_peer_mode_single_gpu_matches_default():
         sd = eng.optimizer_state_dict()
         assert sd["exp_avg"].numel() == eng.n_params and sd["step"] == 4
         params.append((eng.flat_param.clone(), sd["exp_avg_sq"], float(loss.item())))
-    (pa, va, la), (pb, vb, lb) = params
-    assert abs(la - lb) <= 1e-5 * abs(lb)
-    np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), rtol=0, atol=2e-5)     # 4 steps of lr 1e-3; float atomics order differs
-    np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=1e-3, atol=1e-12)
+    pb, vb, lb = params[-1]
+    for pa, va, la in params[:-1]:
+        assert abs(la - lb) <= 1e-5 * abs(lb)
+        np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), rtol=0, atol=2e-5)     # 4 steps of lr 1e-3; float atomics order differs
+        np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=1e-3, atol=1e-12)
 
 
 # ----------------------------------------------------------------------------- two ranks
@@ -125,7 +126,14 @@ def _worker(rank, world, port, out_dir):
     try:
         batches, S = _batches(rank, 5)
         res = {}
-        for mode in ("peer", "nccl"):
+        modes = ["push", "peer", "nccl"]
+        try:   # NVLS needs NVSwitch multicast; exercised when the box has it
+            probe = NAFEngine(_net(dev, seed=rank), lr=1e-3, n_samples=S, exchange="nvls")
+            del probe
+            modes.insert(0, "nvls")
+        except RuntimeError:
+            pass
+        for mode in modes:
             eng = NAFEngine(_net(dev, seed=rank), lr=1e-3, n_samples=S, perturb=True, loss_chunk=100, use_cuda_graph=True, exchange=mode)
             assert eng.exchange_mode == mode, eng.exchange_mode
             for rays, projs, t_rand in batches:
@@ -148,7 +156,9 @@ def test_two_gpu_peer_exchange_matches_nccl(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     res = torch.load(os.path.join(str(tmp_path), "res.pt"))
-    assert res["peer"]["err"] == 0
-    assert res["peer"]["div"] == 0.0 and res["nccl"]["div"] == 0.0       # replicas bit-identical
-    np.testing.assert_allclose(res["peer"]["param"].numpy(), res["nccl"]["param"].numpy(), rtol=0, atol=2e-5)
-    np.testing.assert_allclose(res["peer"]["v"].numpy(), res["nccl"]["v"].numpy(), rtol=2e-3, atol=1e-12)
+    print("exchange modes exercised:", sorted(res))
+    for mode in res:
+        assert res[mode]["err"] == 0 and res[mode]["div"] == 0.0, mode    # no timed-out flag, replicas bit-identical
+        if mode != "nccl":
+            np.testing.assert_allclose(res[mode]["param"].numpy(), res["nccl"]["param"].numpy(), rtol=0, atol=2e-5)
+            np.testing.assert_allclose(res[mode]["v"].numpy(), res["nccl"]["v"].numpy(), rtol=2e-3, atol=1e-12)
