@@ -1,5 +1,5 @@
 set -x
-TAG=${TAG:-r1e}
+TAG=${TAG:-r1f}
 CMD="python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-extra --profile-steps 3"
 timeout 300 $CMD > gpurun_out/prof_plain.log 2>&1 || exit 1
 for k in k_density_bwd_tc k_density_fwd_tc k_adam_dev; do
