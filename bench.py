@@ -100,7 +100,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.05)
+            self._halt.wait(0.01)
 
     def finish(self):
         self._halt.set()
