@@ -180,16 +180,16 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// 8 floats -> one 16-byte chunk of the hi matrix and one of the lo matrix
+// 8 floats -> one 16-byte chunk of the hi matrix and one of the lo matrix (packed conversions: two values per cvt)
 __device__ __forceinline__ void split_chunk(const float *v8, uint4 &hi, uint4 &lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v8[2 * i], h0, l0);
-        split_bf16(v8[2 * i + 1], h1, l1);
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        const float a = v8[2 * i], b = v8[2 * i + 1];
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);                       // .x = a (low half), .y = b
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __low2float(h2), b - __high2float(h2));
+        h[i] = *reinterpret_cast<const uint32_t *>(&h2);
+        l[i] = *reinterpret_cast<const uint32_t *>(&l2);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
