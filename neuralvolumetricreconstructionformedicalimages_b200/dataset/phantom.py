@@ -51,3 +51,44 @@ def phantom_projections(rays: torch.Tensor, ellipsoids) -> torch.Tensor:
         chord = torch.clamp(torch.minimum(t1, far) - torch.maximum(t0, near), min=0.0)
         out += torch.where(disc > 0, v * chord, torch.zeros_like(chord))
     return (out * d.norm(dim=-1)).to(torch.float32).reshape(rays.shape[:-1])
+
+
+# ----------------------------------------------------------------------------- reference pickle schema
+def make_dataset_dict(geometry: dict, n_train: int, n_val: int, ellipsoids=None, amplitude: float = 1.0) -> dict:
+    """A dataset in the schema the reference's TIGREDataset reads (format_data.py:25-58, src/dataset/tigre.py:230-302):
+    geometry block + 'image' + 'full_proj' (complex, A*exp(i*phase): the laminography pipeline trains on the phase) +
+    'train' / 'val' {angles, projections}.  Projections are exact line integrals of the analytic phantom.
+    `geometry` carries DSD, DSO, nDetector, dDetector, nVoxel, dVoxel, offOrigin, offDetector, mode (+ tilt_angle)."""
+    from .geometry import rays_with_near_far
+    geo = ConeGeometry(geometry)
+    ells = ellipsoids if ellipsoids is not None else default_ellipsoids(float(min(geo.sVoxel)) / 2)
+    span = np.pi if geo.mode == "cone" else np.pi
+    tr_angles = np.linspace(0, span, n_train + 1)[:-1]
+    va_angles = np.linspace(0, span, n_val + 1)[:-1] + span / (2 * max(n_val, 1))
+
+    def project(angles):
+        rays = rays_with_near_far(angles, geo, "cpu")
+        return phantom_projections(rays, ells).numpy().astype(np.float32)
+
+    tr, va = project(tr_angles), project(va_angles)
+    data = dict(geometry)
+    data.update(numTrain=n_train, numVal=n_val, accuracy=geometry.get("accuracy", 0.5), filter=geometry.get("filter"),
+                totalAngle=180, startAngle=0, randomAngle=False, convert=False, rescale_slope=1.0, rescale_intercept=0.0,
+                normalize=True, noise=0, tilt_angle=geometry.get("tilt_angle", 0), image=phantom_volume(geo, ells),
+                full_proj=(amplitude * np.exp(1j * tr)).astype(np.complex64),
+                train={"angles": tr_angles, "projections": tr}, val={"angles": va_angles, "projections": va})
+    return data
+
+
+def save_pickle(data: dict, path: str) -> None:
+    import pickle
+    with open(path, "wb") as f:
+        pickle.dump(data, f)
+
+
+def load_pickle(path: str):
+    """-> (data dict, ConeGeometry) of a dataset in the reference's schema."""
+    import pickle
+    with open(path, "rb") as f:
+        data = pickle.load(f)
+    return data, ConeGeometry(data)
