@@ -38,6 +38,29 @@ class PixelSampler:
         # tigre.py:356: only pixels with a non-zero projection value are candidates
         self.valid = [torch.nonzero(projs[p].reshape(-1) != 0).reshape(-1).to(torch.int32) for p in range(P)]
 
+    def draw_epoch(self, n_rays: int, generator=None, projections=None):
+        """The batches of a whole epoch in a handful of batched device ops: for every projection in `projections` (default:
+        all, in order) n_rays valid pixels without replacement.  Returns (pixels [K,N,3] int32, projs [K,N], mask [K,N] uint8).
+        Uniform sampling without replacement = the n_rays smallest of i.i.d. uniform keys over the valid pixels (invalid
+        pixels get a key that sorts last) -- the same distribution as one np.random.choice(replace=False) per item
+        (tigre.py:358), without a host round trip or a launch sequence per iteration."""
+        P, H, W = self.shape
+        dev = self.projs.device
+        sel_p = torch.arange(P, device=dev) if projections is None else torch.as_tensor(projections, device=dev, dtype=torch.long)
+        if not hasattr(self, "_valid_mask"):
+            self._valid_mask = (self.projs.reshape(P, -1) != 0)
+            self._n_valid = self._valid_mask.sum(dim=1)
+        if int(self._n_valid[sel_p].min()) < n_rays:
+            raise ValueError(f"a projection has fewer than n_rays = {n_rays} valid pixels")
+        keys = torch.rand(sel_p.numel(), H * W, device=dev, generator=generator)
+        keys.masked_fill_(~self._valid_mask[sel_p], 2.0)
+        sel = keys.topk(n_rays, dim=1, largest=False, sorted=False).indices                 # [K, N] flat pixel ids
+        row, col = sel // W, sel % W
+        pixels = torch.stack([sel_p[:, None].expand_as(sel), row, col], dim=2).to(torch.int32).contiguous()
+        flat_p = self.projs.reshape(P, -1)[sel_p]
+        flat_m = self.mask.reshape(P, -1)[sel_p]
+        return pixels, torch.gather(flat_p, 1, sel), torch.gather(flat_m, 1, sel)
+
     def draw(self, proj: int, n_rays: int, generator=None):
         """(pixels [N,3] int32, projs [N] fp32, mask [N] uint8) for projection `proj`: n_rays valid pixels without replacement
         (uniform, as np.random.choice(replace=False) at tigre.py:358)."""

@@ -154,6 +154,16 @@ def test_ptycho_mask_and_pixel_sampler(golden):
     assert torch.equal(pr, projs[1].reshape(-1)[flat]) and torch.equal(mk, ps.mask[1].reshape(-1)[flat])
     with pytest.raises(ValueError):
         ps.draw(1, 12 * 17, g)
+    # a whole epoch at once
+    pe, pre, mke = ps.draw_epoch(40, g, projections=[2, 0, 1])
+    assert pe.shape == (3, 40, 3) and pre.shape == (3, 40) and mke.shape == (3, 40) and pe[:, 0, 0].tolist() == [2, 0, 1]
+    for k, pj in enumerate([2, 0, 1]):
+        fl = (pe[k, :, 1].long() * 17 + pe[k, :, 2].long()).numpy()
+        assert len(np.unique(fl)) == 40
+        assert torch.equal(pre[k], projs[pj].reshape(-1)[fl]) and torch.equal(mke[k], ps.mask[pj].reshape(-1)[fl])
+    assert int(pe[2, :, 1].min()) >= 4                                    # projection 1: rows 0..3 never drawn
+    with pytest.raises(ValueError):
+        ps.draw_epoch(12 * 17 - 10, g)
 
 
 def test_pose_table_and_detector_fields(golden):
