@@ -310,6 +310,49 @@ def test_density_backward_stash_and_aggregated_scatter():
 
 
 @both_modes
+@pytest.mark.parametrize("L,C,log2T,H", [(32, 1, 14, 1), (8, 4, 16, 16), (4, 8, 18, 32)])
+def test_density_other_level_dims(mlp_mode, L, C, log2T, H):
+    """Grids with level_dim 1, 4 and 8 (L * C == 32, hashencoder.cu:302-311) through the fused kernels: render forward and
+    backward against the oracle, all arithmetic modes (the table holds dense, wrapped-linear and hashed levels).  32 levels
+    need base_resolution 1: the per-level scale is fixed at 2 (hashencoder.cu:99), so level 31 reaches 2^31 cells and any
+    larger base overflows the uint32 cell index in the reference itself."""
+    torch.manual_seed(2)
+    rng = np.random.default_rng(2)
+    enc = get_encoder("hashgrid", input_dim=3, num_levels=L, level_dim=C, base_resolution=H, log2_hashmap_size=log2T)
+    net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(DEV)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-0.05, 0.05)
+    o_enc = oh.OracleHashEncoder(3, L, C, H, log2T, use_ref=False, normalise="mul_recip")
+    o = naf.OracleDensityNetwork(o_enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid")
+    with torch.no_grad():
+        o_enc.embeddings.copy_(enc.embeddings.cpu())
+        for a, b in zip(o.layers, net.layers):
+            a.weight.copy_(b.weight.cpu())
+            a.bias.copy_(b.bias.cpu())
+    N, S = 70, 40
+    rays = torch.from_numpy(make_rays(N, rng))
+    t_rand = torch.from_numpy(rng.uniform(0, 1, (N, S)).astype(np.float32))
+    w = torch.from_numpy(rng.normal(size=N).astype(np.float32))
+    real = torch.rand
+    torch.rand = lambda *a, **k: t_rand.to(DEV)
+    try:
+        ret = render(rays.to(DEV), net, None, S, 0, True, 409600, 0.0)
+    finally:
+        torch.rand = real
+    (ret["acc"] * w.to(DEV)).sum().backward()
+    oret = naf.render(rays, o, S, True, t_rand=t_rand)
+    (oret["acc"] * w).sum().backward()
+    assert np.array_equal(bits(ret["pts"].cpu().numpy()), bits(oret["pts"].numpy()))
+    np.testing.assert_allclose(ret["acc"].detach().cpu().numpy(), oret["acc"].detach().numpy(), rtol=1e-4, atol=1e-7)
+    # gradients: fp32 SIMT within summation-order noise; tensor-core modes carry the bf16x3 product error (2^-16 per product)
+    # through sums with cancellation, so entries much smaller than the largest get an absolute bound relative to it
+    atol_rel = 2e-5 if mlp_mode == 1 else 2e-4
+    for a, b in zip(net.parameters(), o.parameters()):
+        gb = b.grad.numpy()
+        np.testing.assert_allclose(a.grad.cpu().numpy(), gb, rtol=5e-3, atol=atol_rel * np.abs(gb).max())
+
+
+@both_modes
 def test_density_ragged_and_range(mlp_mode):
     net = _chest_net()
     for P in [1, 127, 128, 129, 1000]:
