@@ -18,8 +18,11 @@ cp "$REF_ROOT/train.py" "$OUT/train.py"
 CU="$OUT/src/encoder/hashencoder/src/hashencoder.cu"
 sed -i 's/inputs\.type()/inputs.scalar_type()/; s/grad\.type()/grad.scalar_type()/' "$CU"
 grep -n "scalar_type()" "$CU"
+# `--no-cuda`: stage the Python only (what bench.py's reference arm needs together with oracle/_ref); the 3-4 minute CUDA
+# pre-build below is only needed by baseline/ref_cuda_bench.py
+if [ "${1:-}" = "--no-cuda" ]; then echo "staged $OUT/src (no CUDA pre-build)"; exit 0; fi
 # pre-build (nvcc cross-compiles without a GPU); the JIT loader of the staged copy is replaced at import time by
-# baseline/ref_cuda_bench.py, which loads this .so instead of compiling on the GPU box
+# baseline/ref_loader.py, which loads this .so instead of compiling on the GPU box
 python - <<PY
 import os, torch
 os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
