@@ -425,23 +425,27 @@ def main():
     final_loss = float(loss.item())
     clocks = sampler.finish()
 
-    # ---------------- end to end: pinned host inputs -> H2D -> step -> D2H of the loss, every step
-    # (train_step copies the pinned host tensors straight into the buffers its graph reads: 3 H2D copies + 1 graph launch)
-    for i in range(3):
-        step(in_h[i], projs_h[i], mask_h[i]).item()
+    # ---------------- end to end: host inputs -> H2D -> step -> D2H of the loss, every step, through the engine's host entry
+    # (NAFEngine.train_step_host: staging in pinned memory, one graph launch = H2D copies + iteration + D2H of the loss,
+    #  stream synchronisation, python float back)
+    def step_host(j):
+        return (eng.train_step_host(projs_h[j], mask_h[j], pixels=in_h[j]) if use_pixels
+                else eng.train_step_host(projs_h[j], mask_h[j], rays=in_h[j]))
+
+    for i in range(4):
+        step_host(i)
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(K):
-        j = (W + i) % n_b
-        host_loss = step(in_h[j], projs_h[j], mask_h[j]).item()      # H2D of the inputs, D2H read of the step's result
+        host_loss = step_host((W + i) % n_b)
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
     h2d = in_h[0].numel() * 4 + projs_h[0].numel() * 4 + mask_h[0].numel()
-    d2h = 4
+    d2h = 8
 
     # ---------------- per-kernel CUDA-event timing (instrumented eager pass, same workload)
     from neuralvolumetricreconstructionformedicalimages_b200.engine import EventTimer

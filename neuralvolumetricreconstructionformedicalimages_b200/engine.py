@@ -452,6 +452,62 @@ class NAFEngine:
             self.step_count += 1
         return s["loss"][0]
 
+    def train_step_host(self, projs, mask=None, pixels=None, rays=None):
+        """One optimisation step fed from HOST memory, result read back to the host: returns the loss as a python float.
+
+        The end-to-end form of train_step: the inputs are copied into pinned staging buffers (a few KB of CPU memcpy), and
+        ONE graph launch performs the H2D copies, the whole iteration and the D2H copy of the loss; the call then waits for
+        the stream.  (train_step with pinned host tensors does the same with separate copy calls and leaves the loss on the
+        device.)"""
+        use_pixels = pixels is not None
+        src = pixels if use_pixels else rays
+        N = src.shape[0]
+        s = self._get_static(N, mask is not None)
+        if use_pixels and s["pixels"] is None:
+            s["pixels"] = torch.zeros(N, 3, device=self.device, dtype=torch.int32)
+        hk = "host_pix" if use_pixels else "host_rays"
+        if s.get(hk) is None:
+            s[hk] = dict(inp=torch.empty((N, 3) if use_pixels else (N, 8), dtype=torch.int32 if use_pixels else torch.float32).pin_memory(),
+                         projs=torch.empty(N, dtype=torch.float32).pin_memory(),
+                         mask=torch.empty(N, dtype=torch.uint8).pin_memory() if mask is not None else None,
+                         loss=torch.zeros(2, dtype=torch.float32).pin_memory())
+        h = s[hk]
+        h["inp"].copy_(src.reshape(h["inp"].shape))
+        h["projs"].copy_(projs.reshape(N))
+        if mask is not None:
+            h["mask"].copy_(mask.reshape(N))
+        with torch.cuda.device(self.device):
+            par = self._parity()
+            in_graph = not (self.world_size > 1 and self.px is None)
+
+            def body(with_optimizer):
+                (s["pixels"] if use_pixels else s["rays"]).copy_(h["inp"], non_blocking=True)
+                s["projs"].copy_(h["projs"], non_blocking=True)
+                if mask is not None:
+                    s["mask"].copy_(h["mask"], non_blocking=True)
+                self._whole_step(s, par, None, None, with_optimizer=with_optimizer, use_pixels=use_pixels)
+                if with_optimizer:
+                    h["loss"].copy_(s["loss"], non_blocking=True)
+
+            key = (N, mask is not None, par, "host", use_pixels)
+            g = self._graphs.get(key)
+            if not self.use_cuda_graph or (g is None and self._eager_runs.get(key, 0) < 1):
+                self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
+                body(True)
+            else:
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        body(in_graph)
+                    self._graphs[key] = g
+                g.replay()
+                if not in_graph:
+                    self._finish_step(par)
+                    h["loss"].copy_(s["loss"], non_blocking=True)
+            self.step_count += 1
+            torch.cuda.current_stream().synchronize()
+        return float(h["loss"][0])
+
     # ------------------------------------------------------------------ inference
     @torch.no_grad()
     def render_projection(self, rays, t_rand=None, perturb=None):

@@ -418,6 +418,19 @@ def test_engine_pixel_batches_equal_ray_batches():
         res.append((float(loss.item()), eng.flat_param.clone()))
     assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
     np.testing.assert_allclose(res[0][1].cpu().numpy(), res[1][1].cpu().numpy(), rtol=0, atol=5e-6)
+    # the host entry (pinned staging + one graph launch incl. H2D / D2H) performs the same steps
+    torch.manual_seed(0)
+    net = _chest_net(table_scale=0.3)
+    eng = NAFEngine(net, lr=1e-3, n_samples=S, perturb=False, loss_chunk=200, use_cuda_graph=True)
+    eng.set_geometry(data["angles"], geo)
+    torch.manual_seed(0)
+    eng2 = NAFEngine(_chest_net(table_scale=0.3), lr=1e-3, n_samples=S, perturb=False, loss_chunk=200, use_cuda_graph=True)
+    eng2.set_geometry(data["angles"], geo)
+    for _ in range(3):
+        lh = eng.train_step_host(projs.cpu(), None, pixels=pixels.cpu())
+        ld = eng2.train_step(None, projs, None, pixels=pixels)
+    assert isinstance(lh, float) and abs(lh - float(ld.item())) <= 1e-5 * abs(lh)
+    np.testing.assert_allclose(eng.flat_param.cpu().numpy(), eng2.flat_param.cpu().numpy(), rtol=0, atol=5e-6)
 
 
 # ----------------------------------------------------------------------------- render
