@@ -379,8 +379,6 @@ class NAFEngine:
         """Inputs -> the static buffers the graph reads (device tensors, or pinned host tensors: one H2D copy each)."""
         N = s["rays"].shape[0]
         if pixels is not None:
-            if s["pixels"] is None:
-                s["pixels"] = torch.zeros(N, 3, device=self.device, dtype=torch.int32)
             s["pixels"].copy_(pixels.reshape(N, 3), non_blocking=True)
         else:
             s["rays"].copy_(rays.reshape(N, 8), non_blocking=True)
@@ -411,9 +409,19 @@ class NAFEngine:
         if s is None:
             d = self.device
             nb = stash_bytes(self.meta, self.table, self.mlp_params, N * self.n_samples) if self.use_stash else 0
-            s = dict(rays=torch.zeros(N, 8, device=d), projs=torch.zeros(N, device=d),
+            # the per-step inputs live in ONE device buffer [rays | pixels | projs | mask] (16-byte aligned regions): a step fed
+            # from the host is one H2D copy of the regions it uses (train_step_host)
+            r16 = lambda n: (n + 15) // 16 * 16
+            o_rays, o_pix = 0, r16(32 * N)
+            o_projs = o_pix + r16(12 * N)
+            o_mask = o_projs + r16(4 * N)
+            packed = torch.zeros(o_mask + r16(N), device=d, dtype=torch.uint8)
+            s = dict(packed=packed, offsets=(o_rays, o_pix, o_projs, o_mask),
+                     rays=packed[o_rays:o_rays + 32 * N].view(torch.float32).view(N, 8),
+                     pixels=packed[o_pix:o_pix + 12 * N].view(torch.int32).view(N, 3),
+                     projs=packed[o_projs:o_projs + 4 * N].view(torch.float32),
                      stash=torch.empty(nb, dtype=torch.uint8, device=d) if nb else None,
-                     mask=torch.ones(N, device=d, dtype=torch.uint8) if with_mask else None, t_rand=None, pixels=None,
+                     mask=packed[o_mask:o_mask + N] if with_mask else None, t_rand=None,
                      loss=torch.zeros(2, device=d), dacc=torch.zeros(N, device=d), acc=torch.zeros(N, device=d))
             self._static[key] = s
         return s
@@ -463,28 +471,30 @@ class NAFEngine:
         src = pixels if use_pixels else rays
         N = src.shape[0]
         s = self._get_static(N, mask is not None)
-        if use_pixels and s["pixels"] is None:
-            s["pixels"] = torch.zeros(N, 3, device=self.device, dtype=torch.int32)
+        o_rays, o_pix, o_projs, o_mask = s["offsets"]
         hk = "host_pix" if use_pixels else "host_rays"
         if s.get(hk) is None:
-            s[hk] = dict(inp=torch.empty((N, 3) if use_pixels else (N, 8), dtype=torch.int32 if use_pixels else torch.float32).pin_memory(),
-                         projs=torch.empty(N, dtype=torch.float32).pin_memory(),
-                         mask=torch.empty(N, dtype=torch.uint8).pin_memory() if mask is not None else None,
+            hp = torch.zeros(s["packed"].numel(), dtype=torch.uint8).pin_memory()      # host mirror of the packed input buffer
+            s[hk] = dict(packed=hp, inp=(hp[o_pix:o_pix + 12 * N].view(torch.int32).view(N, 3) if use_pixels
+                                         else hp[o_rays:o_rays + 32 * N].view(torch.float32).view(N, 8)),
+                         projs=hp[o_projs:o_projs + 4 * N].view(torch.float32), mask=hp[o_mask:o_mask + N],
                          loss=torch.zeros(2, dtype=torch.float32).pin_memory())
         h = s[hk]
         h["inp"].copy_(src.reshape(h["inp"].shape))
         h["projs"].copy_(projs.reshape(N))
         if mask is not None:
             h["mask"].copy_(mask.reshape(N))
+        end = o_mask + N if mask is not None else o_projs + 4 * N
         with torch.cuda.device(self.device):
             par = self._parity()
             in_graph = not (self.world_size > 1 and self.px is None)
 
             def body(with_optimizer):
-                (s["pixels"] if use_pixels else s["rays"]).copy_(h["inp"], non_blocking=True)
-                s["projs"].copy_(h["projs"], non_blocking=True)
-                if mask is not None:
-                    s["mask"].copy_(h["mask"], non_blocking=True)
+                if use_pixels:     # [pixels | projs | mask] are contiguous: one H2D copy
+                    s["packed"][o_pix:end].copy_(h["packed"][o_pix:end], non_blocking=True)
+                else:
+                    s["packed"][o_rays:o_rays + 32 * N].copy_(h["packed"][o_rays:o_rays + 32 * N], non_blocking=True)
+                    s["packed"][o_projs:end].copy_(h["packed"][o_projs:end], non_blocking=True)
                 self._whole_step(s, par, None, None, with_optimizer=with_optimizer, use_pixels=use_pixels)
                 if with_optimizer:
                     h["loss"].copy_(s["loss"], non_blocking=True)
