@@ -612,6 +612,7 @@ int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_
     if (P == 0) return NAFB_OK;
     if (src != NAFB_SRC_RAYS && (acc || z_vals || pts_out)) NAFB_FAIL(NAFB_ERR_INVALID, "density_forward: acc/z_vals/pts_out need the RAYS source");
     cudaStream_t s = (cudaStream_t)stream;
+    if (src == NAFB_SRC_VOXELS) stash = nullptr;            // forward-only source (its tiles are lattice blocks, not point ranges)
     if (g_mlp_mode != 1 && nafb_tc_config_ok(grid, mlp))   // mode 2: warp-specialised forward (producer / MMA / epilogue warps)
         return (g_mlp_mode == 2 ? nafb_launch_fwd_ws : nafb_launch_fwd_tc)(gp, *mlp, sp, src, P, sigma, acc, z_vals, pts_out, flags, stash, s);
 #define CALL(S_, C_) launch_fwd<S_, C_>(gp, *mlp, sp, P, sigma, acc, z_vals, pts_out, flags, s)

@@ -397,13 +397,14 @@ __global__ void __launch_bounds__(NT, FWD_CTAS) k_density_fwd_tc(const GridParam
     uint32_t phase = 0;
     int bad = 0;
 
-    const uint64_t n_tiles = (P + TILE - 1) / TILE;
+    const uint64_t n_tiles = SRC == NAFB_SRC_VOXELS ? voxel_block_tiles(sp) : (P + TILE - 1) / TILE;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t p = tile * TILE + r;
-        const bool valid = p < P;
+        uint64_t p = tile * TILE + r;      // index of the point in the outputs
+        bool valid = p < P;
         float x[3] = {0.f, 0.f, 0.f};
+        if constexpr (SRC == NAFB_SRC_VOXELS) valid = voxel_block_point(sp, tile, (uint32_t)r, x, p);   // 4 x 4 x 8 blocks of the lattice
         if (valid) {
-            fetch_point<SRC>(sp, p, x);
+            if constexpr (SRC != NAFB_SRC_VOXELS) fetch_point<SRC>(sp, p, x);
             if (!(x[0] >= -sp.bound && x[0] <= sp.bound && x[1] >= -sp.bound && x[1] <= sp.bound && x[2] >= -sp.bound && x[2] <= sp.bound))
                 bad |= 1;
             if (SRC == NAFB_SRC_RAYS && pts_out && half == 0) {
@@ -889,7 +890,7 @@ int launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams 
         if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_forward(tc): %s", cudaGetErrorString(e));
         configured = true;
     }
-    const uint64_t n_tiles = (P + TILE - 1) / TILE;
+    const uint64_t n_tiles = SRC == NAFB_SRC_VOXELS ? (uint64_t)((sp.i1 - sp.i0 + 3) / 4) * ((sp.n2 + 3) / 4) * ((sp.n3 + 7) / 8) : (P + TILE - 1) / TILE;
     const uint64_t cap = (uint64_t)nafb_sm_count() * FWD_CTAS;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
     k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags, stash, nafb_debug_flags());

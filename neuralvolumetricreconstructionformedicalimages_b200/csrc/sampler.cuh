@@ -154,6 +154,27 @@ __device__ __forceinline__ Jitter jitter_for(const SamplerParams &sp, uint32_t r
     return j;
 }
 
+// Voxel source, blocked traversal: a 128-point tile is a 4 x 4 x 8 block of the lattice (i, j, k = row & 7 fastest) instead of
+// 128 consecutive voxels of one k-line, so that the points of a tile (and of a warp: an 4 x 8 patch in j, k) share grid
+// cells -- and therefore table sectors -- in all three directions on every level whose cells are larger than a voxel.
+// Same voxel centres (voxel_coord), same output index; only the order of evaluation changes.
+__device__ __forceinline__ uint64_t voxel_block_tiles(const SamplerParams &sp) {
+    return (uint64_t)((sp.i1 - sp.i0 + 3) / 4) * ((sp.n2 + 3) / 4) * ((sp.n3 + 7) / 8);
+}
+__device__ __forceinline__ bool voxel_block_point(const SamplerParams &sp, uint64_t tile, uint32_t r, float (&x)[3], uint64_t &out_index) {
+    const uint32_t nbk = (sp.n3 + 7) / 8, nbj = (sp.n2 + 3) / 4;
+    const uint32_t bk = (uint32_t)(tile % nbk);
+    const uint64_t t2 = tile / nbk;
+    const uint32_t bj = (uint32_t)(t2 % nbj), bi = (uint32_t)(t2 / nbj);
+    const uint32_t k = bk * 8 + (r & 7u), j = bj * 4 + ((r >> 3) & 3u), i = sp.i0 + bi * 4 + (r >> 5);
+    if (i >= sp.i1 || j >= sp.n2 || k >= sp.n3) return false;
+    x[0] = voxel_coord(i, sp.n1, sp.s1);
+    x[1] = voxel_coord(j, sp.n2, sp.s2);
+    x[2] = voxel_coord(k, sp.n3, sp.s3);
+    out_index = ((uint64_t)(i - sp.i0) * sp.n2 + j) * sp.n3 + k;
+    return true;
+}
+
 // Fetch point p of the launch (world coordinates). For RAYS also yields ray/sample index.
 template <int SRC>
 __device__ __forceinline__ void fetch_point(const SamplerParams &sp, uint64_t p, float (&x)[3]) {
