@@ -2,9 +2,13 @@
 // configuration every shipped YAML uses: L*C == 32 encoding, 4 layers x 32 hidden, skip at
 // layer 2, out_dim 1 (reference src/network/network.py:34-58, config/*.yaml).
 //
-// One CTA = 256 threads = one 128-point tile at a time (persistent over tiles).
+// One CTA = one 128-point tile at a time (persistent over tiles); 256 epilogue threads (+ one MMA-issue warp in backward).
 //   thread t:  row r = t & 127 (sample point, == TMEM lane), half = t >> 7 owns feature
 //              columns [16*half, 16*half+16) of every 32-wide activation of its point.
+// Forward: sampling / ray generation (sampler.cuh) -> gather (pair-merged 128-bit loads) -> 3 MMA phases -> head -> ray
+// integral; the encodings are left in the "stash" for backward.  Backward: stash -> forward chain -> head gradient ->
+// 3 backward phases; d(encoding) stays in TMEM and is scattered (warp-aggregated, pair-merged) from the wait slots of the
+// NEXT tile.  DESIGN.md section 4 has the measurements behind each of these choices.
 // Activations are written ONCE, by the thread that owns the point, as bf16 (hi, lo) pairs in the
 // canonical no-swizzle UMMA layout (umma.cuh) and consumed in place by the tensor core:
 //   forward      h_l   = lrelu(X . W_l^T + b)        A = X  (K-major)      B = W_l  (K-major)
@@ -19,7 +23,8 @@
 #include "umma.cuh"
 
 // profiling knobs (env NAFB_DEBUG_SKIP, read once): bit 0 = skip the gradient scatter, bit 1 = skip the table
-// gather (synthetic encodings).  Results are wrong with any bit set; used only to attribute kernel time.
+// gather (synthetic encodings), bit 4 = no warp aggregation, bit 5 = phase time stamps of the backward kernel,
+// bits 8-13 / 16-21 = aggregation thresholds.  Results are wrong with bits 0/1 set; used only to attribute kernel time.
 int nafb_debug_flags();
 
 namespace {

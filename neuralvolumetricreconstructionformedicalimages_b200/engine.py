@@ -1,12 +1,15 @@
 """NAFEngine -- the opt-in fused training / inference driver ("an opt-in
 fused train_step entry that bypasses autograd").
 
-One optimisation step is four kernel launches, captured once in a CUDA graph:
+One optimisation step is five kernel launches, captured once in a CUDA graph (nothing changes between replays: step
+count, learning rate and the sampler's RNG seed live in a device-resident state the kernels read and advance):
 
-    density_forward (rays -> sampling -> gather -> MLP -> sum sigma*delta -> acc[N])
-    mse_loss        (masked chunk-wise MSE + d loss / d acc)
-    density_backward(recompute -> MLP backward -> scatter into the flat gradient) + reduce
-    adam_step       (fused dense Adam over ONE flat vector [table | MLP], zeroing the gradient)
+    density_forward (detector pixels or rays -> ray generation -> sampling -> gather -> MLP -> sum sigma*delta -> acc[N];
+                     leaves the encodings in the stash)
+    mse_loss        (masked chunk-wise MSE + d loss / d acc; clears acc)
+    density_backward(stash -> MLP forward/backward on tensor cores -> aggregated scatter into the flat gradient) + reduce_partials
+    adam_step_dev   (fused dense Adam over ONE flat vector [table | MLP], zeroing the gradient) -- or, on several GPUs, the
+                    fused exchange kernel (reduce-scatter + Adam + all-gather over NVLink peer memory)
 
 It takes the place of ``Trainer.train_step`` (reference src/trainer.py:134-142) +
 ``BasicTrainer.compute_loss`` (train.py:48-135) for the shipped configurations.  Parameters stay
@@ -14,7 +17,7 @@ ordinary ``nn.Parameter`` views of the flat vector, so ``state_dict()`` / ``ckpt
 with the reference layout (encoder.embeddings, layers.i.weight/bias).
 
 Multi-GPU: one process per GPU, rays sharded across ranks, parameters replicated.  The step's one exchange
-(sum of the flat gradient over ranks -> Adam -> identical parameters everywhere) runs in one of two ways:
+(sum of the flat gradient over ranks -> Adam -> identical parameters everywhere) runs in one of these ways:
 
   exchange="push" (default when it can be set up): ONE kernel over NVLink peer memory (csrc/exchange.cu): every rank owns a
       slice of the flat vector; ranks push their gradient slices into the owners' staging areas, the owner adds them in rank
