@@ -671,3 +671,66 @@ def test_engine_train_steps_vs_oracle(mlp_mode):
         assert d < 2e-4, d  # Adam normalises the update to ~lr per step; sign flips on ~0 gradients bound the drift
     sd = net.state_dict()
     assert sd["encoder.embeddings"].shape == (7131219, 2) and sd["layers.2.weight"].shape == (32, 64)
+
+
+# ----------------------------------------------------------------------------- memory safety (compute-sanitizer is not available on the pool)
+def _guarded(numel, dtype=torch.float32, guard=4096, fill=None):
+    """A buffer of `numel` elements inside a larger allocation whose margins hold a sentinel."""
+    big = torch.empty(numel + 2 * guard, dtype=dtype, device=DEV)
+    sentinel = 0x5A if dtype == torch.uint8 else (-(2 ** 30) if dtype == torch.int32 else -1.2345e30)
+    big.fill_(sentinel)
+    view = big[guard:guard + numel]
+    if fill is not None:
+        view.fill_(fill)
+    return big, view, sentinel, guard
+
+
+def _guards_intact(big, numel, sentinel, guard):
+    lo, hi = big[:guard], big[guard + numel:]
+    return bool((lo == sentinel).all().item()) and bool((hi == sentinel).all().item())
+
+
+@both_modes
+def test_fused_kernels_write_only_inside_their_buffers(mlp_mode):
+    """Every output / scratch buffer of the fused forward and backward is placed between sentinel margins; ragged sizes
+    (last tile partly empty, rays straddling tiles and warps).  The margins must come back untouched."""
+    L_ = _lib.lib()
+    rng = np.random.default_rng(5)
+    net = _chest_net(table_scale=0.3)
+    meta = net.fused_meta()
+    N, S = 37, 70                                   # P = 2590 points: 20 full tiles + 30 points
+    P = N * S
+    rays = torch.from_numpy(make_rays(N, rng)).to(DEV)
+    t_rand = torch.rand(N, S, device=DEV)
+    n_tab = net.encoder.embeddings.numel()
+    bufs = {}
+    bufs["table"] = _guarded(n_tab)
+    bufs["table"][1].copy_(net.encoder.embeddings.detach().reshape(-1))
+    table = bufs["table"][1].view(-1, 2)
+    ps = [p.detach().contiguous() for p in net.flat_params()]
+    grid, mlp = meta.grid(table), meta.mlp(ps)
+    smp = meta.sampler(rays=rays.data_ptr(), t_rand=t_rand.data_ptr(), n_rays=N, n_samples=S, perturb=1)
+    nstash = int(L_.nafb_density_stash_bytes(ctypes.byref(grid), ctypes.byref(mlp), P))
+    for name, numel, dtype, fill in [("sigma", P, torch.float32, None), ("acc", N, torch.float32, 0.0), ("z", P, torch.float32, None),
+                                     ("pts", 3 * P, torch.float32, None), ("flags", 1, torch.int32, 0),
+                                     ("stash", max(nstash, 16), torch.uint8, None), ("gtab", n_tab, torch.float32, 0.0)]:
+        bufs[name] = _guarded(numel, dtype, fill=fill)
+    stash = bufs["stash"][1] if nstash else None
+    _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, _lib.ptr(bufs["sigma"][1]),
+                                       _lib.ptr(bufs["acc"][1]), _lib.ptr(bufs["z"][1]), _lib.ptr(bufs["pts"][1]), _lib.ptr(bufs["flags"][1]),
+                                       _lib.ptr(stash), _lib.stream_ptr()))
+    nws = int(L_.nafb_density_backward_workspace_bytes(ctypes.byref(mlp)))
+    bufs["ws"] = _guarded(nws, torch.uint8)
+    gps = []
+    for i, p in enumerate(ps):
+        bufs[f"gp{i}"] = _guarded(p.numel(), fill=0.0)
+        gps.append(bufs[f"gp{i}"][1].view_as(p))
+    grads = _lib.make_mlp_grads(gps[0::2], gps[1::2])
+    dacc = torch.randn(N, device=DEV)
+    _lib.check(L_.nafb_density_backward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, _lib.ptr(dacc),
+                                        _lib.ptr(bufs["gtab"][1]), ctypes.byref(grads), _lib.ptr(bufs["ws"][1]), _lib.ptr(stash), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    for name, (big, view, sentinel, guard) in bufs.items():
+        assert _guards_intact(big, view.numel(), sentinel, guard), f"write outside the {name} buffer"
+    assert torch.isfinite(bufs["sigma"][1]).all() and torch.isfinite(bufs["gtab"][1]).all() and int(bufs["flags"][1].item()) == 0
+    assert float(bufs["gtab"][1].abs().sum()) > 0 and all(float(g.abs().sum()) > 0 for g in gps)
