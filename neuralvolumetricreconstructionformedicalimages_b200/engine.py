@@ -523,15 +523,41 @@ class NAFEngine:
 
     # ------------------------------------------------------------------ inference
     @torch.no_grad()
-    def render_projection(self, rays, t_rand=None, perturb=None):
-        """acc [N] for rays [N,8] (forward only; reference eval path train.py:235-240)."""
+    def render_projection(self, rays=None, t_rand=None, perturb=None, pixels=None):
+        """acc [N] for rays [N,8] -- or for detector pixels [N,3] (projection, row, col), the rays being generated in the
+        kernel (set_geometry) -- forward only; the reference's eval path renders a whole view this way (train.py:235-240)."""
         perturb = self.perturb if perturb is None else perturb
-        rays = rays.reshape(-1, 8).contiguous()
-        if perturb and t_rand is None:
-            t_rand = torch.rand(rays.shape[0], self.n_samples, device=self.device)
-        out = density_forward(self.meta, self.table, self.mlp_params, rays=rays, t_rand=t_rand, n_samples=self.n_samples, perturb=perturb,
-                              want_acc=True, want_sigma=False)
-        return out["acc"]
+        if pixels is not None:
+            pixels = pixels.reshape(-1, 3).to(torch.int32).contiguous()
+            N = pixels.shape[0]
+        else:
+            rays = rays.reshape(-1, 8).contiguous()
+            N = rays.shape[0]
+        smp = self._ray_sampler(rays, pixels, t_rand if perturb else None)
+        smp.perturb = int(bool(perturb))
+        if not perturb:
+            smp.rng_state = None
+        acc = torch.zeros(N, device=self.device, dtype=torch.float32)
+        grid, mlp = self.meta.grid(self.table), self.meta.mlp(self.mlp_params)
+        _lib.check(_lib.lib().nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, None, _lib.ptr(acc),
+                                                   None, None, None, None, _lib.stream_ptr()))
+        return acc
+
+    @torch.no_grad()
+    def eval_step(self, view: int, proj_gt: torch.Tensor, image_gt: torch.Tensor, n_voxel, s_half, perturb=None):
+        """The reference's eval_step (train.py:220-286) without its host round trips: render projection `view` (every
+        detector pixel, rays generated in-kernel), query the whole volume, score both on the device.
+        proj_gt [H,W], image_gt [n1,n2,n3].  Returns {"proj_mse", "proj_psnr", "psnr_3d", "ssim_3d", "projs_pred", "image_pred"}."""
+        from .utils import get_mse, get_psnr, get_psnr_3d, get_ssim_3d
+        H, W = proj_gt.shape
+        row, col = torch.meshgrid(torch.arange(H, device=self.device), torch.arange(W, device=self.device), indexing="ij")
+        pixels = torch.stack([torch.full_like(row, int(view)), row, col], dim=-1).reshape(-1, 3).to(torch.int32)
+        projs_pred = self.render_projection(pixels=pixels, perturb=perturb).reshape(H, W)
+        image_pred = self.voxel_query(n_voxel, s_half)
+        out = {"proj_mse": float(get_mse(projs_pred, proj_gt)), "proj_psnr": float(get_psnr(projs_pred, proj_gt)),
+               "psnr_3d": get_psnr_3d(image_pred, image_gt), "projs_pred": projs_pred, "image_pred": image_pred}
+        out["ssim_3d"] = get_ssim_3d(image_pred, image_gt) if min(image_gt.shape) >= 7 else float("nan")
+        return out
 
     @torch.no_grad()
     def voxel_query(self, n_voxel, s_half, slab=None, out=None):

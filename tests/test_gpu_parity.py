@@ -734,3 +734,30 @@ def test_fused_kernels_write_only_inside_their_buffers(mlp_mode):
         assert _guards_intact(big, view.numel(), sentinel, guard), f"write outside the {name} buffer"
     assert torch.isfinite(bufs["sigma"][1]).all() and torch.isfinite(bufs["gtab"][1]).all() and int(bufs["flags"][1].item()) == 0
     assert float(bufs["gtab"][1].abs().sum()) > 0 and all(float(g.abs().sum()) > 0 for g in gps)
+
+
+def test_eval_step_full_view_and_volume_vs_oracle():
+    """NAFEngine.eval_step (train.py:220-286 on the device): the rendered view (rays generated in-kernel for every detector
+    pixel) and the volume equal the oracle's; the scores equal the oracle's metric restatements."""
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import phantom as PH
+    data = G.chest50_like(n_voxel=16, n_detector=24, n_proj=4)
+    geo = G.ConeGeometry(data)
+    ells = PH.default_ellipsoids(float(geo.sVoxel[0]) / 2)
+    rays_all = G.rays_with_near_far(data["angles"], geo, "cpu")
+    projs = PH.phantom_projections(rays_all, ells)
+    vol_gt = torch.from_numpy(PH.phantom_volume(geo, ells))
+    net = _chest_net(table_scale=0.3)
+    eng = NAFEngine(net, n_samples=48, perturb=False, use_cuda_graph=False)
+    eng.set_geometry(data["angles"], geo)
+    view = 2
+    res = eng.eval_step(view, projs[view].to(DEV), vol_gt.to(DEV), [int(v) for v in geo.nVoxel], G.voxel_half_extent(geo))
+    o = _oracle_net(net)
+    with torch.no_grad():
+        oret = naf.render(rays_all[view].reshape(-1, 8), o, 48, False)
+        ovol = naf.run_network(torch.from_numpy(G.get_voxels(geo).astype(np.float32)), o, 409600).squeeze(-1)
+    np.testing.assert_allclose(res["projs_pred"].cpu().numpy().reshape(-1), oret["acc"].numpy(), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(res["image_pred"].cpu().numpy(), ovol.numpy(), rtol=2e-5, atol=2e-6)
+    assert abs(res["psnr_3d"] - naf.psnr_3d(ovol.numpy(), vol_gt.numpy())) < 1e-3
+    assert abs(res["ssim_3d"] - naf.ssim_3d(ovol.numpy(), vol_gt.numpy())) < 1e-4
+    assert abs(res["proj_mse"] - float(((oret["acc"].reshape(24, 24) - projs[view]) ** 2).mean())) < 1e-6
