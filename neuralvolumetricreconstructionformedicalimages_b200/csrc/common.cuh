@@ -78,6 +78,25 @@ __device__ __forceinline__ CellTerms cell_terms3(const LevelParams &lp, uint32_t
     t.c[0] = z * m2; t.c[1] = t.c[0] + m2;
     return t;
 }
+// all 8 corner entries of the cell, corner idx = dx | dy << 1 | dz << 2, with ONE warp-uniform decision per level (instead
+// of a select per corner): a hashed level always has a power-of-two size (it is hashed because (res+1)^3 exceeds 2^log2T);
+// a linear level is masked when its size is a power of two (the wrapped "linear-overflow" levels) and otherwise dense, where
+// the index of an in-range position needs no reduction at all.
+__device__ __forceinline__ void cell_entries8(const LevelParams &lp, const CellTerms &t, uint32_t (&e)[8]) {
+    if (lp.hashed) {
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) e[i] = (t.a[i & 1u] ^ t.b[(i >> 1) & 1u] ^ t.c[i >> 2]) & lp.mask;
+    } else if (lp.mask) {
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) e[i] = (t.a[i & 1u] + t.b[(i >> 1) & 1u] + t.c[i >> 2]) & lp.mask;
+    } else {
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) {
+            const uint32_t l = t.a[i & 1u] + t.b[(i >> 1) & 1u] + t.c[i >> 2];
+            e[i] = l < lp.size ? l : l % lp.size;
+        }
+    }
+}
 __device__ __forceinline__ uint32_t cell_entry(const LevelParams &lp, const CellTerms &t, uint32_t dx, uint32_t dy, uint32_t dz) {
     const uint32_t h = t.a[dx] ^ t.b[dy] ^ t.c[dz], l = t.a[dx] + t.b[dy] + t.c[dz];
     return wrap_index(lp.hashed ? h : l, lp);

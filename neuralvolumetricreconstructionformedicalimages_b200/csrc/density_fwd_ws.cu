@@ -91,9 +91,11 @@ __device__ __forceinline__ void gather_chunk_ws(const LevelParams *__restrict__ 
         for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
         const uint32_t par = addr_parity8(tab);
         const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
+        uint32_t e[8];
+        cell_entries8(lp, ct, e);
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j)
-            load_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v[li][2 * j], v[li][2 * j + 1]);
+            load_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[li][2 * j], v[li][2 * j + 1]);
     };
     auto consume = [&](const int li) {
         const float scale = lvs[chunk * LPC + li].scale;

@@ -91,9 +91,11 @@ __device__ __forceinline__ void gather_half(const GridParams &gp, const float (&
         for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
         const uint32_t par = addr_parity8(tab);
         const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
+        uint32_t e[8];
+        cell_entries8(lp, ct, e);
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j)   // (y, z) corner; the two x-neighbours share one access when adjacent + aligned
-            load_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v[li][2 * j], v[li][2 * j + 1]);
+            load_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[li][2 * j], v[li][2 * j + 1]);
     };
     auto consume = [&](const int li) {
         const float scale = gp.lv[half * LH + li].scale;
@@ -155,6 +157,8 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
     locate(x1, lp.scale, g[1], f[1]);
     locate(x2, lp.scale, g[2], f[2]);
     const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
+    uint32_t e[8];
+    cell_entries8(lp, ct, e);
     umma::tmem_wait_ld();
     if (agg_max_runs > 0) {
         // runs of equal cells among consecutive lanes (invalid lanes: a run of their own, never issued)
@@ -189,8 +193,7 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
             if (head && valid) {
 #pragma unroll
                 for (uint32_t j = 0; j < 4; ++j)
-                    red_add_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v[2 * j],
-                                          v[2 * j + 1]);
+                    red_add_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[2 * j], v[2 * j + 1]);
             }
             return;
         }
@@ -205,7 +208,7 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
                 v0[c] = __fmul_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.0f, f[0]), (j & 1u) ? f[1] : __fsub_rn(1.0f, f[1])), (j >> 1) ? f[2] : __fsub_rn(1.0f, f[2])), ge[c]);
                 v1[c] = __fmul_rn(__fmul_rn(__fmul_rn(f[0], (j & 1u) ? f[1] : __fsub_rn(1.0f, f[1])), (j >> 1) ? f[2] : __fsub_rn(1.0f, f[2])), ge[c]);
             }
-            red_add_entry_pair<C>(tab, par, cell_entry(lp, ct, 0, j & 1u, j >> 1), cell_entry(lp, ct, 1, j & 1u, j >> 1), v0, v1);
+            red_add_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v0, v1);
         }
     }
 }
@@ -227,10 +230,11 @@ __device__ __noinline__ void gather_half_to_smem(const LevelParams *__restrict__
         locate(x1, lp.scale, g[1], f[1]);
         locate(x2, lp.scale, g[2], f[2]);
         const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
+        uint32_t e[8];
+        cell_entries8(lp, ct, e);
         float v[8][C];
 #pragma unroll
-        for (uint32_t idx = 0; idx < 8; ++idx)
-            load_entry<C>(tab, cell_entry(lp, ct, idx & 1u, (idx >> 1) & 1u, idx >> 2), v[idx]);
+        for (uint32_t idx = 0; idx < 8; ++idx) load_entry<C>(tab, e[idx], v[idx]);
         float res[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) res[c] = 0.f;

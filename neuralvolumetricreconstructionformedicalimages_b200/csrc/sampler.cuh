@@ -23,6 +23,7 @@ struct SamplerParams {
     int32_t perturb;
     uint32_t n1, n2, n3, i0, i1;
     double s1, s2, s3;
+    double vstep1, vstep2, vstep3;   // np.linspace step (s - (-s)) / (n - 1), evaluated once on the host in float64
     float bound, inv_2bound, clamp;
     float lin_step;  // fl(1 / (S-1))
 };
@@ -94,10 +95,9 @@ __device__ __forceinline__ float ray_point(float o, float d, float z, float c) {
 }
 
 // np.linspace(-s, s, n)[i] in float64, then the fp32 cast of tigre.py:277
-__device__ __forceinline__ float voxel_coord(uint32_t i, uint32_t n, double s) {
+__device__ __forceinline__ float voxel_coord(uint32_t i, uint32_t n, double s, double step) {
     if (n == 1) return (float)(-s);
     if (i == n - 1) return (float)s;
-    const double step = __ddiv_rn(__dsub_rn(s, -s), (double)(n - 1));
     return (float)__dadd_rn(__dmul_rn((double)i, step), -s);
 }
 
@@ -168,9 +168,9 @@ __device__ __forceinline__ bool voxel_block_point(const SamplerParams &sp, uint6
     const uint32_t bj = (uint32_t)(t2 % nbj), bi = (uint32_t)(t2 / nbj);
     const uint32_t k = bk * 8 + (r & 7u), j = bj * 4 + ((r >> 3) & 3u), i = sp.i0 + bi * 4 + (r >> 5);
     if (i >= sp.i1 || j >= sp.n2 || k >= sp.n3) return false;
-    x[0] = voxel_coord(i, sp.n1, sp.s1);
-    x[1] = voxel_coord(j, sp.n2, sp.s2);
-    x[2] = voxel_coord(k, sp.n3, sp.s3);
+    x[0] = voxel_coord(i, sp.n1, sp.s1, sp.vstep1);
+    x[1] = voxel_coord(j, sp.n2, sp.s2, sp.vstep2);
+    x[2] = voxel_coord(k, sp.n3, sp.s3, sp.vstep3);
     out_index = ((uint64_t)(i - sp.i0) * sp.n2 + j) * sp.n3 + k;
     return true;
 }
@@ -193,9 +193,9 @@ __device__ __forceinline__ void fetch_point(const SamplerParams &sp, uint64_t p,
         const uint32_t i = sp.i0 + (uint32_t)(p / plane);
         const uint32_t rem = (uint32_t)(p - (uint64_t)(i - sp.i0) * plane);
         const uint32_t j = rem / sp.n3, k = rem - j * sp.n3;
-        x[0] = voxel_coord(i, sp.n1, sp.s1);
-        x[1] = voxel_coord(j, sp.n2, sp.s2);
-        x[2] = voxel_coord(k, sp.n3, sp.s3);
+        x[0] = voxel_coord(i, sp.n1, sp.s1, sp.vstep1);
+        x[1] = voxel_coord(j, sp.n2, sp.s2, sp.vstep2);
+        x[2] = voxel_coord(k, sp.n3, sp.s3, sp.vstep3);
     }
 }
 
@@ -234,6 +234,9 @@ static inline int nafb_make_sampler_params(const nafb_sampler *s, int src, Sampl
     p.n_rays = s->n_rays; p.n_samples = s->n_samples; p.perturb = s->perturb;
     p.n1 = s->n1; p.n2 = s->n2; p.n3 = s->n3; p.i0 = s->i0; p.i1 = s->i1;
     p.s1 = s->s1; p.s2 = s->s2; p.s3 = s->s3;
+    p.vstep1 = s->n1 > 1 ? (s->s1 - (-s->s1)) / (double)(s->n1 - 1) : 0.0;
+    p.vstep2 = s->n2 > 1 ? (s->s2 - (-s->s2)) / (double)(s->n2 - 1) : 0.0;
+    p.vstep3 = s->n3 > 1 ? (s->s3 - (-s->s3)) / (double)(s->n3 - 1) : 0.0;
     p.bound = s->bound;
     p.inv_2bound = 1.0f / (2.0f * s->bound);   // see normalise01: fl(1 / fl(2*size)); the doubling is exact
     p.clamp = s->clamp;
