@@ -73,3 +73,64 @@ def test_psnr_after_fixed_iterations_matches_oracle():
     assert abs(psnr_c - psnr_o) <= 0.1, (psnr_c, psnr_o)
     # and the two volumes themselves agree closely
     assert naf.psnr_3d(vol_c, vol_o) > 40.0
+
+
+def test_psnr_after_fixed_iterations_matches_the_reference_cuda_build():
+    """Same protocol against the REFERENCE ITSELF on the GPU (staged copy + its CUDA extension, baseline/_ref): the
+    reference's render / DensityNetwork / HashEncoder / calc_mse_loss + torch.optim.Adam and the fused engine train from the
+    same initialisation on the same batches and uniforms; PSNR-3D of the two reconstructions within 0.1 dB."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from baseline import ref_loader
+    if not ref_loader.available("cuda"):
+        pytest.skip("the reference's CUDA build is not staged on this machine (baseline/stage_ref.sh)")
+    r_get_encoder, r_get_network, r_render, r_calc_mse_loss = ref_loader.import_reference("cuda")
+    torch.manual_seed(0)
+    rng = np.random.default_rng(0)
+    data = G.chest50_like(n_voxel=32, n_detector=64, n_proj=20)
+    geo = G.ConeGeometry(data)
+    ells = PH.default_ellipsoids(float(geo.sVoxel[0]) / 2)
+    vol_gt = PH.phantom_volume(geo, ells)
+    rays_all = G.rays_with_near_far(data["angles"], geo, "cpu").reshape(-1, 8)
+    projs_all = PH.phantom_projections(rays_all, ells)
+    rays_all, projs_all = rays_all.to(DEV), projs_all.to(DEV)
+
+    enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
+    net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(DEV)
+    r_enc = r_get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
+    r_net = r_get_network("mlp")(r_enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(DEV)
+    with torch.no_grad():
+        r_net.encoder.embeddings.copy_(net.encoder.embeddings)
+        for a, b in zip(r_net.layers, net.layers):
+            a.weight.copy_(b.weight)
+            a.bias.copy_(b.bias)
+    r_opt = torch.optim.Adam(r_net.parameters(), lr=2e-3, betas=(0.9, 0.999))
+    eng = NAFEngine(net, lr=2e-3, n_samples=N_SAMPLES, perturb=True, loss_chunk=None, use_cuda_graph=True)
+    real = torch.rand
+    for it in range(STEPS):
+        pix = torch.from_numpy(rng.choice(rays_all.shape[0], N_RAYS, replace=False)).to(DEV)
+        rays, projs = rays_all[pix], projs_all[pix]
+        t_rand = torch.from_numpy(rng.uniform(0, 1, (N_RAYS, N_SAMPLES)).astype(np.float32)).to(DEV)
+        lc = eng.train_step(rays, projs, None, t_rand)
+        torch.rand = lambda *a, **k: t_rand.clone()
+        try:
+            r_opt.zero_grad()
+            ret = r_render(rays, r_net, None, N_SAMPLES, 0, True, 409600, 0.0)
+        finally:
+            torch.rand = real
+        loss = {"loss": 0.0}
+        r_calc_mse_loss(loss, projs, ret["acc"])
+        loss["loss"].backward()
+        r_opt.step()
+    np.testing.assert_allclose(float(lc.item()), float(loss["loss"].item()), rtol=0.05)
+    n = [int(v) for v in geo.nVoxel]
+    vol_c = eng.voxel_query(n, G.voxel_half_extent(geo)).cpu().numpy()
+    with torch.no_grad():
+        vox = torch.from_numpy(G.get_voxels(geo).astype(np.float32)).to(DEV)
+        vol_r = r_net(vox.reshape(-1, 3)).reshape(n).cpu().numpy()
+    psnr_c, psnr_r = naf.psnr_3d(vol_c, vol_gt), naf.psnr_3d(vol_r, vol_gt)
+    print(f"PSNR_3d after {STEPS} iterations: engine {psnr_c:.3f} dB, reference CUDA build {psnr_r:.3f} dB")
+    assert abs(psnr_c - psnr_r) <= 0.1, (psnr_c, psnr_r)
+    assert naf.psnr_3d(vol_c, vol_r) > 40.0
