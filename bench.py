@@ -215,6 +215,31 @@ def cpu_reference_run(steps, warmup, n_rays=N_RAYS):
                 n_rays=n_rays, kind=kind)
 
 
+def reference_cuda_numbers():
+    """The reference's own CUDA build timed on this GPU (baseline/ref_cuda_bench.py in a subprocess, ~2 s), when it is staged
+    under baseline/_ref: the denominator of BASELINE.json's ">= 20x the reference's CUDA build" target, reported next to our
+    number in the same run.  None when the staging is absent."""
+    import subprocess
+    script = os.path.join(ROOT, "baseline", "ref_cuda_bench.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "build")):
+        return None
+    try:
+        r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                           env=dict(os.environ, REF_STEPS="20", REF_WARMUP="5"))
+        out = {}
+        for l in r.stdout.splitlines():
+            if l.startswith("{"):
+                d = json.loads(l)
+                out[d["variant"]] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"]}
+        if not out:
+            return None
+        out["note"] = ("the reference's render / DensityNetwork / HashEncoder (its CUDA extension, 2-line compile fix) / calc_mse_loss + "
+                       "torch.optim.Adam on the same workload: 'chunked' = train.py's 200-ray chunk loop, 'one_call' = one render() per step")
+        return out
+    except Exception:
+        return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -536,6 +561,10 @@ def main():
         }
         if extra is not None:
             line["workloads"] = extra
+        if world == 1 and not args.no_cpu_baseline:
+            rc = reference_cuda_numbers()
+            if rc:
+                line["reference_cuda"] = rc
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=8, warmup=2)
             line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
