@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 7
+#define NAFB_ABI_VERSION 8
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -72,6 +72,18 @@ int nafb_hash_encode_forward(const nafb_grid *grid, const float *inputs, float *
 int nafb_hash_encode_backward(const nafb_grid *grid, const float *grad, const float *inputs,
                               float *grad_table, uint32_t B, int grad_layout, int calc_grad_inputs,
                               const float *dy_dx, float *grad_inputs, nafb_stream_t stream);
+
+/* The same two operations for the other storage types the reference's FFI dispatches on
+ * (AT_DISPATCH_FLOATING_TYPES_AND_HALF, hashencoder.cu:392,423): every tensor -- table, inputs, outputs, dy_dx, grad,
+ * grad_table, grad_inputs -- has the element type `dtype`; `table` / `grad_table` replace grid->table, which is ignored.
+ * fp16 is what `@custom_fwd(cast_inputs=torch.half)` (hashgrid.py:12) hands the op under autocast; its table gradient
+ * leaves as half2 reductions (hashencoder.cu:257-263).  NAFB_DTYPE_F32 forwards to the functions above. */
+enum nafb_dtype { NAFB_DTYPE_F32 = 0, NAFB_DTYPE_F16 = 1, NAFB_DTYPE_F64 = 2 };
+int nafb_hash_encode_forward_dtype(const nafb_grid *grid, int dtype, const void *table, const void *inputs, void *outputs,
+                                   uint32_t B, int out_layout, int calc_grad_inputs, void *dy_dx, nafb_stream_t stream);
+int nafb_hash_encode_backward_dtype(const nafb_grid *grid, int dtype, const void *grad, const void *inputs, void *grad_table,
+                                    uint32_t B, int grad_layout, int calc_grad_inputs, const void *dy_dx, void *grad_inputs,
+                                    nafb_stream_t stream);
 
 /* One fused pass min/max over a float buffer -> out2[0] = min, out2[1] = max
  * (the range check of hashgrid.py:122 without two separate reductions). */

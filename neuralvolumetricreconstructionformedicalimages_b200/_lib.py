@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnafb200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 NAFB_MAX_LEVELS = 32
 NAFB_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
@@ -77,6 +77,10 @@ _SIGNATURES = {
     "nafb_last_error": (ctypes.c_char_p, []),
     "nafb_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
     "nafb_hash_encode_forward": (ctypes.c_int, [ctypes.POINTER(Grid), c_f32p, c_f32p, u32, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_void_p]),
+    "nafb_hash_encode_forward_dtype": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, u32,
+                                                      ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "nafb_hash_encode_backward_dtype": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, u32,
+                                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nafb_hash_encode_backward": (ctypes.c_int, [ctypes.POINTER(Grid), c_f32p, c_f32p, c_f32p, u32, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p, ctypes.c_void_p]),
     "nafb_minmax": (ctypes.c_int, [c_f32p, u64, c_f32p, ctypes.c_void_p]),
     "nafb_density_stash_bytes": (u64, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), u64]),
@@ -149,6 +153,21 @@ def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
         kind = "an int" if dtype == torch.int32 else "a float32"
         raise RuntimeError(f"{name} must be {kind} tensor (got {t.dtype})")
     return t
+
+
+DTYPES = {torch.float32: 0, torch.float16: 1, torch.float64: 2}   # enum nafb_dtype
+
+
+def require_floating(t: torch.Tensor, name: str, like: torch.Tensor = None) -> int:
+    """CHECK_CUDA / CHECK_CONTIGUOUS / CHECK_IS_FLOATING (hashencoder.cu:17-20) for the dtype-dispatched op; with `like`, the
+    dtype must also be `like`'s -- the reference dispatches on one tensor and `data_ptr<scalar_t>()` of the others raises
+    RuntimeError on a mismatch (hashencoder.cu:392-394).  Returns the nafb_dtype code."""
+    require_cuda(t, name, dtype=None)
+    if t.dtype not in DTYPES:
+        raise RuntimeError(f"{name} must be a floating tensor")
+    if like is not None and t.dtype != like.dtype:
+        raise RuntimeError(f"expected scalar type {like.dtype} but found {t.dtype} ({name})")
+    return DTYPES[t.dtype]
 
 
 def ptr(t):

@@ -10,7 +10,8 @@ extension at the same call site on the same GPU.
 Ownership and semantics are the reference's: the caller allocates every tensor; ``outputs`` [L,B,C] and ``dy_dx`` are
 overwritten; ``grad_embeddings`` (pre-zeroed by hashgrid.py:59) and ``grad_inputs`` are accumulated into; wrong device /
 layout / dtype raise RuntimeError like the TORCH_CHECKs of hashencoder.cu:17-20; unsupported C or D raise with the
-reference's message (hashencoder.cu:310,324).  fp32 only.
+reference's message (hashencoder.cu:310,324).  fp32, fp16 and fp64 like AT_DISPATCH_FLOATING_TYPES_AND_HALF (:392,423):
+every tensor of a call must have the dtype of ``inputs`` (forward) / ``grad`` (backward).
 """
 from __future__ import annotations
 
@@ -34,26 +35,26 @@ def _grid(embeddings, offsets, D, C, L, H):
 class _backend:
     @staticmethod
     def hash_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, H, calc_grad_inputs, dy_dx):
-        for t, name in ((inputs, "inputs"), (embeddings, "embeddings"), (outputs, "outputs")):
-            _lib.require_cuda(t, name)
-        if calc_grad_inputs:
-            _lib.require_cuda(dy_dx, "dy_dx")
+        dtype = _lib.require_floating(inputs, "inputs")
+        for t, name in ((embeddings, "embeddings"), (outputs, "outputs"), (dy_dx, "dy_dx")):   # dy_dx is checked even when unused (:385)
+            _lib.require_floating(t, name, like=inputs)
         g, keep = _grid(embeddings, offsets, D, C, L, H)
         with torch.cuda.device(inputs.device):
-            _lib.check(_lib.lib().nafb_hash_encode_forward(ctypes.byref(g), _lib.ptr(inputs), _lib.ptr(outputs), int(B), _lib.LAYOUT_LBC,
-                                                           int(bool(calc_grad_inputs)), _lib.ptr(dy_dx) if calc_grad_inputs else None,
-                                                           _lib.stream_ptr()))
+            _lib.check(_lib.lib().nafb_hash_encode_forward_dtype(ctypes.byref(g), dtype, _lib.ptr(embeddings), _lib.ptr(inputs), _lib.ptr(outputs),
+                                                                 int(B), _lib.LAYOUT_LBC, int(bool(calc_grad_inputs)),
+                                                                 _lib.ptr(dy_dx) if calc_grad_inputs else None, _lib.stream_ptr()))
 
     @staticmethod
     def hash_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, H, calc_grad_inputs, dy_dx, grad_inputs):
-        for t, name in ((grad, "grad"), (inputs, "inputs"), (embeddings, "embeddings"), (grad_embeddings, "grad_embeddings")):
-            _lib.require_cuda(t, name)
+        dtype = _lib.require_floating(grad, "grad")
+        for t, name in ((inputs, "inputs"), (embeddings, "embeddings"), (grad_embeddings, "grad_embeddings")):
+            _lib.require_floating(t, name, like=grad)
         g, keep = _grid(grad_embeddings, offsets, D, C, L, H)
         with torch.cuda.device(inputs.device):
-            _lib.check(_lib.lib().nafb_hash_encode_backward(ctypes.byref(g), _lib.ptr(grad), _lib.ptr(inputs), _lib.ptr(grad_embeddings), int(B),
-                                                            _lib.LAYOUT_BLC, int(bool(calc_grad_inputs)),
-                                                            _lib.ptr(dy_dx) if calc_grad_inputs else None,
-                                                            _lib.ptr(grad_inputs) if calc_grad_inputs else None, _lib.stream_ptr()))
+            _lib.check(_lib.lib().nafb_hash_encode_backward_dtype(ctypes.byref(g), dtype, _lib.ptr(grad), _lib.ptr(inputs), _lib.ptr(grad_embeddings),
+                                                                  int(B), _lib.LAYOUT_BLC, int(bool(calc_grad_inputs)),
+                                                                  _lib.ptr(dy_dx) if calc_grad_inputs else None,
+                                                                  _lib.ptr(grad_inputs) if calc_grad_inputs else None, _lib.stream_ptr()))
 
 
 __all__ = ["_backend"]

@@ -21,13 +21,13 @@ class _hash_encode(Function):
     The [L,B,C] -> [B,L*C] permute of hashgrid.py:40 is folded into the kernel's store."""
 
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.half)   # hashgrid.py:12: fp16 op under autocast, else the tensors' own type
     def forward(ctx, inputs, embeddings, offsets, base_resolution, calc_grad_inputs=False):
         L_ = _lib.lib()
         inputs = inputs.contiguous()
         embeddings = embeddings.contiguous()
-        _lib.require_cuda(inputs, "inputs")
-        _lib.require_cuda(embeddings, "embeddings")
+        dtype = _lib.require_floating(inputs, "inputs")
+        _lib.require_floating(embeddings, "embeddings", like=inputs)
         if offsets.dtype != torch.int32:
             raise RuntimeError("offsets must be an int tensor")
         offsets_np = np.ascontiguousarray(offsets.detach().cpu().numpy(), dtype=np.int32)
@@ -42,9 +42,10 @@ class _hash_encode(Function):
             dy_dx = torch.zeros(1, device=inputs.device, dtype=inputs.dtype)
         grid = _lib.make_grid(embeddings, offsets_np, D, C, H)
         with torch.cuda.device(inputs.device):
-            _lib.check(L_.nafb_hash_encode_forward(ctypes.byref(grid), _lib.ptr(inputs), _lib.ptr(outputs), B, _lib.LAYOUT_BLC,
-                                                   int(bool(calc_grad_inputs)), _lib.ptr(dy_dx), _lib.stream_ptr()))
+            _lib.check(L_.nafb_hash_encode_forward_dtype(ctypes.byref(grid), dtype, _lib.ptr(embeddings), _lib.ptr(inputs), _lib.ptr(outputs), B,
+                                                         _lib.LAYOUT_BLC, int(bool(calc_grad_inputs)), _lib.ptr(dy_dx), _lib.stream_ptr()))
         ctx.save_for_backward(inputs, embeddings, dy_dx)
+        ctx.dtype = dtype
         ctx.offsets_np = offsets_np
         ctx.dims = [B, D, C, L, H]
         ctx.calc_grad_inputs = calc_grad_inputs
@@ -54,17 +55,18 @@ class _hash_encode(Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad):
         L_ = _lib.lib()
-        grad = grad.contiguous()
         inputs, embeddings, dy_dx = ctx.saved_tensors
+        grad = grad.contiguous()
+        _lib.require_floating(grad, "grad", like=inputs)
         B, D, C, L, H = ctx.dims
         calc_grad_inputs = ctx.calc_grad_inputs
         grad_embeddings = torch.zeros_like(embeddings)
         grad_inputs = torch.zeros_like(inputs) if calc_grad_inputs else None
         grid = _lib.make_grid(embeddings, ctx.offsets_np, D, C, H)
         with torch.cuda.device(inputs.device):
-            _lib.check(L_.nafb_hash_encode_backward(ctypes.byref(grid), _lib.ptr(grad), _lib.ptr(inputs), _lib.ptr(grad_embeddings), B,
-                                                    _lib.LAYOUT_BLC, int(bool(calc_grad_inputs)), _lib.ptr(dy_dx),
-                                                    _lib.ptr(grad_inputs), _lib.stream_ptr()))
+            _lib.check(L_.nafb_hash_encode_backward_dtype(ctypes.byref(grid), ctx.dtype, _lib.ptr(grad), _lib.ptr(inputs), _lib.ptr(grad_embeddings),
+                                                          B, _lib.LAYOUT_BLC, int(bool(calc_grad_inputs)), _lib.ptr(dy_dx),
+                                                          _lib.ptr(grad_inputs), _lib.stream_ptr()))
         return grad_inputs, grad_embeddings, None, None, None
 
 

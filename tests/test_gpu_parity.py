@@ -192,6 +192,90 @@ def test_backend_shim_vs_the_reference_cuda_extension(chest_table_unit):
     np.testing.assert_allclose(gis[0], gis[1], rtol=1e-5, atol=1e-6 * np.abs(gis[1]).max())
 
 
+def _reference_extension():
+    import importlib.util
+    import os
+    bd = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "build")
+    so = [f for f in os.listdir(bd) if f.endswith(".so")] if os.path.isdir(bd) else []
+    if not so:
+        pytest.skip("the reference's CUDA extension is not staged on this machine")
+    spec = importlib.util.spec_from_file_location("_hash_encoder", os.path.join(bd, so[0]))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    return ref
+
+
+@pytest.mark.parametrize("dtype,D,C,L,H,log2T", [
+    (torch.float16, 3, 2, 16, 16, 19), (torch.float16, 2, 4, 8, 16, 15), (torch.float16, 3, 1, 8, 8, 14), (torch.float16, 3, 8, 4, 4, 12),
+    (torch.float64, 3, 2, 16, 16, 19), (torch.float64, 2, 8, 6, 8, 12), (torch.float64, 3, 1, 8, 8, 14),
+])
+def test_backend_shim_fp16_fp64_vs_the_reference_cuda_extension(dtype, D, C, L, H, log2T):
+    """The other storage types of the FFI (AT_DISPATCH_FLOATING_TYPES_AND_HALF, hashencoder.cu:392,423) against the reference's
+    compiled extension at the same call site.  Forward and the defined part of dy_dx: bit-exact.  Table gradient: bit-exact for a
+    single point (every entry receives one contribution); for a batch the half2 / double atomics arrive in arbitrary order in both
+    implementations -> fp16: rtol 3e-2 + atol 2^-8 x max (hundreds of half-rounded additions per coarse entry, each order its own
+    rounding path), fp64: rtol 1e-12."""
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder.backend import _backend as ours
+    ref = _reference_extension()
+    rng = np.random.default_rng(5)
+    offs = oh.level_offsets(L, H, log2T, D)
+    table = torch.from_numpy(rng.uniform(-1, 1, (int(offs[-1]), C))).to(DEV).to(dtype)
+    offsets = torch.from_numpy(offs).to(DEV)
+    for B in (1, 3000):
+        x = torch.from_numpy(rng.uniform(0, 1, (B, D))).to(DEV).to(dtype)
+        if B > 8:
+            x[:4] = torch.tensor([[0.] * D, [1.] * D, [0.5] * D, [0.3333] * D], device=DEV).to(dtype)
+        outs, dys = [], []
+        for be in (ours, ref):
+            out = torch.zeros(L, B, C, device=DEV, dtype=dtype)
+            dy = torch.zeros(B, L * D * C, device=DEV, dtype=dtype)
+            be.hash_encode_forward(x, table, offsets, out, B, D, C, L, H, True, dy)
+            torch.cuda.synchronize()
+            outs.append(out.cpu().numpy()); dys.append(dy.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1]) and np.abs(outs[1].astype(np.float64)).max() > 0.1
+        d0, d1 = dys[0].reshape(B, L, D, C), dys[1].reshape(B, L, D, C)
+        assert np.array_equal(d0[:, :, D - 1], d1[:, :, D - 1])          # other axes: reference UB, see the fp32 test
+        grad = torch.from_numpy(rng.normal(size=(B, L * C))).to(DEV).to(dtype)
+        gts, gis = [], []
+        for be in (ours, ref):
+            gt = torch.zeros_like(table)
+            gi = torch.zeros(B, D, device=DEV, dtype=dtype)
+            be.hash_encode_backward(grad, x, table, offsets, gt, B, D, C, L, H, True, torch.from_numpy(dys[1]).to(DEV), gi)
+            torch.cuda.synchronize()
+            gts.append(gt.cpu().numpy().astype(np.float64)); gis.append(gi.cpu().numpy().astype(np.float64))
+        assert np.array_equal(gis[0], gis[1])                               # sequential per thread in both: bit-exact
+        if B == 1:
+            assert np.array_equal(gts[0], gts[1]) and np.count_nonzero(gts[1]) > 0
+        elif dtype == torch.float16:
+            np.testing.assert_allclose(gts[0], gts[1], rtol=3e-2, atol=2.0 ** -8 * np.abs(gts[1]).max())
+        else:
+            np.testing.assert_allclose(gts[0], gts[1], rtol=1e-12, atol=1e-13 * np.abs(gts[1]).max())
+    # dtype mismatch raises like data_ptr<scalar_t>() does in the reference
+    with pytest.raises(RuntimeError):
+        ours.hash_encode_forward(x.float(), table, offsets, out, B, D, C, L, H, False, dy)
+
+
+def test_hash_encoder_under_autocast_runs_the_fp16_op():
+    """hashgrid.py:12 `@custom_fwd(cast_inputs=torch.half)`: under autocast the op sees half inputs and a half copy of the
+    table and returns half; the table gradient comes back in the parameter's fp32 through autograd's cast."""
+    torch.manual_seed(0)
+    enc = HashEncoder().to(DEV)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-1, 1)
+    x = (torch.rand(2048, 3, device=DEV) * 2 - 1) * 0.3
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = enc(x, 0.3)
+    assert y.dtype == torch.float16
+    y32 = enc(x, 0.3)
+    assert y32.dtype == torch.float32
+    # the fp16 op against the fp32 op on the same (half-rounded) positions and table: they differ by the output rounding only
+    x01 = (x + 0.3) / 0.6
+    y_ref = hash_encode(x01.half().float(), enc.embeddings.detach().half().float(), enc.offsets, 16)
+    np.testing.assert_allclose(y.detach().float().cpu().numpy(), y_ref.detach().cpu().numpy(), rtol=0, atol=2.0 ** -11)
+    y.float().square().sum().backward()
+    assert enc.embeddings.grad is not None and enc.embeddings.grad.dtype == torch.float32 and float(enc.embeddings.grad.abs().max()) > 0
+
+
 def test_hash_errors():
     L_ = _lib.lib()
     offs = oh.level_offsets(4, 4, 8, 3)

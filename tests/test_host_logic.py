@@ -115,7 +115,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == _lib.exported_symbols()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.nafb_abi_version() == 7
+    assert L.nafb_abi_version() == 8
     # struct layouts agree with the C header (sizes computed by the C compiler)
     import subprocess
     import tempfile
