@@ -472,11 +472,13 @@ __global__ void __launch_bounds__(TILE, 2) k_density_bwd(const GridParams gp, co
     for (int i = threadIdx.x; i < lo.total; i += blockDim.x) mine[i] = dWs[i];
 }
 
-// gW/gb += sum over CTAs of the partials.  Block = 32 outputs x 8 slices of the CTA range; every slice sums its CTAs in
-// order, the 8 slice sums are combined in order: the summation tree is fixed (deterministic), loads are coalesced.
-__global__ void __launch_bounds__(256) k_reduce_partials(const nafb_mlp mp, const nafb_mlp_grads gr, const float *__restrict__ partials,
-                                                         int n_blocks) {
-    __shared__ float part[8][33];
+// gW/gb += sum over CTAs of the partials.  Block = 32 outputs x 32 slices of the CTA range (1024 threads): a slice sums its
+// CTAs in order with four independent loads in flight (about three L2 round trips for 296 CTAs instead of nine), the 32 slice
+// sums are combined by a fixed tree: the summation order is a function of n_blocks only (deterministic), loads are coalesced.
+constexpr int RP_SLICES = 32;
+__global__ void __launch_bounds__(32 * RP_SLICES) k_reduce_partials(const nafb_mlp mp, const nafb_mlp_grads gr, const float *__restrict__ partials,
+                                                                    int n_blocks) {
+    __shared__ float part[RP_SLICES][33];
     const MlpLayout lo = make_layout(mp);
     const int j = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + j;
@@ -484,19 +486,27 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const nafb_mlp mp, cons
     if (i < lo.total) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int b = k;
-        for (; b + 24 < n_blocks; b += 32) {
-            s0 += partials[(size_t)b * lo.total + i];
-            s1 += partials[(size_t)(b + 8) * lo.total + i];
-            s2 += partials[(size_t)(b + 16) * lo.total + i];
-            s3 += partials[(size_t)(b + 24) * lo.total + i];
+        for (; b + 3 * RP_SLICES < n_blocks; b += 4 * RP_SLICES) {
+            s0 += __ldcg(partials + (size_t)b * lo.total + i);
+            s1 += __ldcg(partials + (size_t)(b + RP_SLICES) * lo.total + i);
+            s2 += __ldcg(partials + (size_t)(b + 2 * RP_SLICES) * lo.total + i);
+            s3 += __ldcg(partials + (size_t)(b + 3 * RP_SLICES) * lo.total + i);
         }
-        for (; b < n_blocks; b += 8) s0 += partials[(size_t)b * lo.total + i];
-        s = (s0 + s1) + (s2 + s3);
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;   // at most three left
+        if (b < n_blocks) t0 = __ldcg(partials + (size_t)b * lo.total + i);
+        if (b + RP_SLICES < n_blocks) t1 = __ldcg(partials + (size_t)(b + RP_SLICES) * lo.total + i);
+        if (b + 2 * RP_SLICES < n_blocks) t2 = __ldcg(partials + (size_t)(b + 2 * RP_SLICES) * lo.total + i);
+        s = ((s0 + s1) + (s2 + s3)) + ((t0 + t1) + t2);
     }
     part[k][j] = s;
     __syncthreads();
+#pragma unroll
+    for (int w = RP_SLICES / 2; w >= 1; w >>= 1) {
+        if (k < w) part[k][j] += part[k + w][j];
+        __syncthreads();
+    }
     if (k != 0 || i >= lo.total) return;
-    s = ((part[0][j] + part[1][j]) + (part[2][j] + part[3][j])) + ((part[4][j] + part[5][j]) + (part[6][j] + part[7][j]));
+    s = part[0][j];
     for (int l = 0; l < lo.n_layers; ++l) {
         const int nw = lo.in[l] * lo.out[l];
         if (i >= lo.woff[l] && i < lo.woff[l] + nw) { if (gr.gW[l]) gr.gW[l][i - lo.woff[l]] += s; return; }
@@ -576,7 +586,7 @@ int launch_bwd(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp
     const int grid = bwd_grid(lo, n_tiles);
     k_density_bwd<SRC, C><<<grid, TILE, smem, s>>>(gp, mp, sp, P, dsig, grad_table, partials);
     NAFB_CHECK_LAUNCH("density_backward");
-    k_reduce_partials<<<(lo.total + 31) / 32, 256, 0, s>>>(mp, gr, partials, grid);
+    k_reduce_partials<<<(lo.total + 31) / 32, 32 * RP_SLICES, 0, s>>>(mp, gr, partials, grid);
     NAFB_CHECK_LAUNCH("density_backward(reduce)");
     return NAFB_OK;
 }
@@ -650,7 +660,7 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
         const MlpLayout lo = make_layout(*mlp);
         long long *stamps = reinterpret_cast<long long *>((char *)workspace + partials_bytes(lo));
         if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps, grid_tc, s))) return rc;
-        k_reduce_partials<<<(lo.total + 31) / 32, 256, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
+        k_reduce_partials<<<(lo.total + 31) / 32, 32 * RP_SLICES, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
         NAFB_CHECK_LAUNCH("density_backward(reduce)");
         return NAFB_OK;
     }

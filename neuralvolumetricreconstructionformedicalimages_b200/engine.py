@@ -175,6 +175,23 @@ class PeerExchange:
                 b.release()
 
 
+class PendingLoss:
+    """The loss of a step enqueued by NAFEngine.train_step_host(wait=False): `result()` waits for that step and returns the float."""
+    __slots__ = ("_event", "_buf", "_value")
+
+    def __init__(self, event, buf):
+        self._event, self._buf, self._value = event, buf, None
+
+    def done(self) -> bool:
+        return self._value is not None or self._event.query()
+
+    def result(self) -> float:
+        if self._value is None:
+            self._event.synchronize()
+            self._value = float(self._buf[0])
+        return self._value
+
+
 class NAFEngine:
     def __init__(self, net: DensityNetwork, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, n_samples=192, perturb=True, loss_chunk=None,
                  use_cuda_graph=True, process_group=None, use_stash=True, exchange="auto", seed=None):
@@ -204,6 +221,7 @@ class NAFEngine:
         self._init_state(seed)
         self._graphs = {}
         self._eager_runs = {}
+        self._host_seq = 0
         self._static = {}
 
     # ------------------------------------------------------------------ flat parameter vector
@@ -463,26 +481,36 @@ class NAFEngine:
             self.step_count += 1
         return s["loss"][0]
 
-    def train_step_host(self, projs, mask=None, pixels=None, rays=None):
+    HOST_SLOTS = 3   # pinned staging slots of train_step_host: a step can be enqueued while the previous one is still running
+
+    def train_step_host(self, projs, mask=None, pixels=None, rays=None, wait=True):
         """One optimisation step fed from HOST memory, result read back to the host: returns the loss as a python float.
 
-        The end-to-end form of train_step: the inputs are copied into pinned staging buffers (a few KB of CPU memcpy), and
-        ONE graph launch performs the H2D copies, the whole iteration and the D2H copy of the loss; the call then waits for
-        the stream.  (train_step with pinned host tensors does the same with separate copy calls and leaves the loss on the
-        device.)"""
+        The end-to-end form of train_step: the inputs are copied into a pinned staging slot (a few KB of CPU memcpy), and
+        ONE graph launch performs the H2D copies, the whole iteration and the D2H copy of the loss into the slot; the call
+        then waits for the stream.  (train_step with pinned host tensors does the same with separate copy calls and leaves
+        the loss on the device.)
+
+        wait=False returns a PendingLoss instead of waiting: `.result()` gives the float once the step has run.  The staging
+        slots rotate (HOST_SLOTS), so the host can stage and enqueue step k+1 while step k computes -- read the loss of step
+        k after enqueueing step k+1 and the copies and the launch latency disappear behind the kernels."""
         use_pixels = pixels is not None
         src = pixels if use_pixels else rays
         N = src.shape[0]
         s = self._get_static(N, mask is not None)
         o_rays, o_pix, o_projs, o_mask = s["offsets"]
-        hk = "host_pix" if use_pixels else "host_rays"
+        slot = self._host_seq % self.HOST_SLOTS
+        self._host_seq += 1
+        hk = ("host_pix" if use_pixels else "host_rays", slot)
         if s.get(hk) is None:
             hp = torch.zeros(s["packed"].numel(), dtype=torch.uint8).pin_memory()      # host mirror of the packed input buffer
             s[hk] = dict(packed=hp, inp=(hp[o_pix:o_pix + 12 * N].view(torch.int32).view(N, 3) if use_pixels
                                          else hp[o_rays:o_rays + 32 * N].view(torch.float32).view(N, 8)),
                          projs=hp[o_projs:o_projs + 4 * N].view(torch.float32), mask=hp[o_mask:o_mask + N],
-                         loss=torch.zeros(2, dtype=torch.float32).pin_memory())
+                         loss=torch.zeros(2, dtype=torch.float32).pin_memory(), event=torch.cuda.Event(), pending=None)
         h = s[hk]
+        if h["pending"] is not None:
+            h["pending"].result()      # the launch that last used this slot has read its inputs and written its loss
         h["inp"].copy_(src.reshape(h["inp"].shape))
         h["projs"].copy_(projs.reshape(N))
         if mask is not None:
@@ -502,10 +530,11 @@ class NAFEngine:
                 if with_optimizer:
                     h["loss"].copy_(s["loss"], non_blocking=True)
 
-            key = (N, mask is not None, par, "host", use_pixels)
+            shape_key = (N, mask is not None, par, "host", use_pixels)
+            key = shape_key + (slot,)
             g = self._graphs.get(key)
-            if not self.use_cuda_graph or (g is None and self._eager_runs.get(key, 0) < 1):
-                self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
+            if not self.use_cuda_graph or self._eager_runs.get(shape_key, 0) < 1:
+                self._eager_runs[shape_key] = self._eager_runs.get(shape_key, 0) + 1
                 body(True)
             else:
                 if g is None:
@@ -518,8 +547,9 @@ class NAFEngine:
                     self._finish_step(par)
                     h["loss"].copy_(s["loss"], non_blocking=True)
             self.step_count += 1
-            torch.cuda.current_stream().synchronize()
-        return float(h["loss"][0])
+            h["event"].record()
+        h["pending"] = PendingLoss(h["event"], h["loss"])
+        return h["pending"].result() if wait else h["pending"]
 
     # ------------------------------------------------------------------ inference
     @torch.no_grad()

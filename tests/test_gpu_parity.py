@@ -561,6 +561,15 @@ def test_engine_pixel_batches_equal_ray_batches():
         ld = eng2.train_step(None, projs, None, pixels=pixels)
     assert isinstance(lh, float) and abs(lh - float(ld.item())) <= 1e-5 * abs(lh)
     np.testing.assert_allclose(eng.flat_param.cpu().numpy(), eng2.flat_param.cpu().numpy(), rtol=0, atol=5e-6)
+    # pipelined form: steps enqueued without waiting (rotating staging slots, different inputs per step so that a slot overwritten
+    # too early would show), losses collected afterwards == the same steps one by one
+    batches = [(torch.from_numpy(rng.uniform(0, 0.05, N).astype(np.float32)), torch.from_numpy(np.roll(pix, k + 1, axis=0).copy())) for k in range(8)]
+    pending = [eng.train_step_host(pj, None, pixels=px, wait=False) for pj, px in batches]
+    sync = [float(eng2.train_step(None, pj.to(DEV), None, pixels=px.to(DEV)).item()) for pj, px in batches]
+    got = [p_.result() for p_ in pending]
+    assert all(p_.done() for p_ in pending)
+    np.testing.assert_allclose(got, sync, rtol=1e-5)
+    np.testing.assert_allclose(eng.flat_param.cpu().numpy(), eng2.flat_param.cpu().numpy(), rtol=0, atol=5e-6)
 
 
 # ----------------------------------------------------------------------------- render
