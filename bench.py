@@ -457,7 +457,7 @@ def main():
         return (eng.train_step_host(projs_h[j], mask_h[j], pixels=in_h[j]) if use_pixels
                 else eng.train_step_host(projs_h[j], mask_h[j], rays=in_h[j]))
 
-    for i in range(6):     # first use runs eagerly, then one graph capture per staging slot
+    for i in range(12):    # first use of a gradient parity runs eagerly, then one graph capture per (parity, staging slot)
         step_host(i)
     barrier()
     t0 = time.perf_counter()
