@@ -102,16 +102,20 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0.):
     raw [N,S,out_dim], z_vals [N,S], rays_d [N,3] -> acc [N], weights [N,S]."""
     if raw.shape[-1] not in (1, 2):
         raise NotImplementedError("Wrong raw shape")
+    clean = raw
     if raw_noise_std > 0.:
+        # the noise enters the line integral only (render.py:196-201); the weights below are taken from the un-noised prediction
         noise = (torch.randn(raw[..., 0].shape) * raw_noise_std).to(raw.device)  # render.py:197-199 (CPU generator)
         raw = torch.cat([(raw[..., :1] + noise[..., None]), raw[..., 1:]], -1)
     rays = torch.zeros(rays_d.shape[0], 8, device=rays_d.device, dtype=torch.float32)
     rays[:, 3:6] = rays_d
     acc, absdiff = _RayIntegral.apply(raw, z_vals, rays)
-    if raw.shape[-1] == 1:
+    if clean.shape[-1] == 1:
+        if clean is not raw:
+            absdiff = torch.cat([torch.full_like(clean[:, :1, -1], 1e-10), torch.abs(clean[:, 1:, -1] - clean[:, :-1, -1])], dim=-1).detach()
         weights = absdiff / torch.max(absdiff)
     else:  # with jac
-        weights = raw[..., 1] / torch.max(raw[..., 1])
+        weights = clean[..., 1] / torch.max(clean[..., 1])
     return acc, weights
 
 
