@@ -177,7 +177,9 @@ int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_
 /* Backward of the above.  dsigma [P] (src POINTS) or dacc [N] (src RAYS: dsigma is derived as
  * dacc[r] * delta[r,i] in-kernel).  Recomputes the forward activations from the points (and the
  * stash, when given), accumulates MLP gradients and scatters into grad_table.
- *   workspace: nafb_density_backward_workspace_bytes() bytes of device scratch. */
+ *   workspace: nafb_density_backward_workspace_bytes() bytes of device scratch, ZERO-FILLED before its first use and not shared by
+ *   launches that may run concurrently (its tail holds the two words of the backward kernel's grid barrier, which the kernel
+ *   leaves zero again). */
 uint64_t nafb_density_backward_workspace_bytes(const nafb_mlp *mlp);
 int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src,
                           const float *dsigma_or_dacc, float *grad_table, const nafb_mlp_grads *grads,

@@ -28,7 +28,7 @@ uint64_t nafb_tc_stash_bytes(uint64_t n_points);
 int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
                        float *pts, int32_t *flags, void *stash, cudaStream_t s);
 int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
-                       float *grad_table, float *partials, const void *stash, long long *stamps, int grid, cudaStream_t s);
+                       float *grad_table, float *partials, const void *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s);
 int nafb_tc_bwd_grid(uint64_t n_tiles);
 int nafb_launch_fwd_ws(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
                        float *pts, int32_t *flags, void *stash, cudaStream_t s);
@@ -639,7 +639,7 @@ int nafb_set_mlp_mode(int mode) {
 uint64_t nafb_density_backward_workspace_bytes(const nafb_mlp *mlp) {
     if (!mlp) return 0;
     const MlpLayout lo = make_layout(*mlp);
-    return partials_bytes(lo) + 4096;   // + debug area (phase time stamps of the tensor-core kernel)
+    return partials_bytes(lo) + 4096 + 64;   // + debug area (phase time stamps of the tensor-core kernel) + grid-barrier words
 }
 
 int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src, const float *dsigma_or_dacc,
@@ -659,10 +659,17 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
         const int grid_tc = nafb_tc_bwd_grid((P + TILE - 1) / TILE);
         const MlpLayout lo = make_layout(*mlp);
         long long *stamps = reinterpret_cast<long long *>((char *)workspace + partials_bytes(lo));
-        if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps, grid_tc, s))) return rc;
-        k_reduce_partials<<<(lo.total + 31) / 32, 32 * RP_SLICES, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
-        NAFB_CHECK_LAUNCH("density_backward(reduce)");
-        return NAFB_OK;
+        // (the tensor-core kernel reduces the per-CTA MLP gradients itself, behind a grid-wide barrier: no second launch)
+        static int separate = -1;   // debug knob: NAFB_BWD_REDUCE=kernel -> the reduction as a separate launch
+        if (separate < 0) { const char *e = getenv("NAFB_BWD_REDUCE"); separate = e && e[0] == 'k'; }
+        if (separate) {
+            nafb_mlp_grads none = {};
+            if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps, grid_tc, none, s))) return rc;
+            k_reduce_partials<<<(lo.total + 31) / 32, 32 * RP_SLICES, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
+            NAFB_CHECK_LAUNCH("density_backward(reduce)");
+            return NAFB_OK;
+        }
+        return nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps, grid_tc, *grads, s);
     }
 #define CALL(S_, C_) launch_bwd<S_, C_>(gp, *mlp, sp, P, dsigma_or_dacc, grad_table, *grads, (float *)workspace, s)
     switch (gp.C) {

@@ -550,7 +550,7 @@ template <int SRC, int C>
 __global__ void __launch_bounds__(NT_B, 2) k_density_bwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           const float *__restrict__ dsig_or_dacc, float *__restrict__ grad_table,
                                                           float *__restrict__ partials, const uint8_t *__restrict__ stash, long long *__restrict__ dbg_stamps,
-                                                          const int dbg) {
+                                                          const int dbg, const nafb_mlp_grads gr, uint32_t *__restrict__ sync) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *A_hi = smem, *A_lo = A_hi + BX_HALF;
     uint8_t *W_hi = A_lo + BX_HALF, *W_lo = W_hi + W_HALF;
@@ -883,6 +883,69 @@ __global__ void __launch_bounds__(NT_B, 2) k_density_bwd_tc(const GridParams gp,
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, T_COLS);
+
+    // ================= gW / gb += sum over the CTAs' rows.  One grid-wide barrier replaces a separate reduction kernel: the grid
+    // is at most 2 CTAs per SM (nafb_tc_bwd_grid) and resident at once, so every CTA can wait for all rows and then sum its
+    // share of the columns -- units of 16 columns x 18 row slices; a slice adds its rows in order with four loads in flight, the 18
+    // slice sums are added in order: the summation tree is a function of the grid size only (deterministic).
+    // sync[0] counts arrivals, sync[1] departures; the last CTA to leave clears both (the workspace starts zero-filled).
+    if (sync == nullptr) return;   // the caller reduces the rows with a separate launch (debug knob NAFB_BWD_REDUCE=kernel)
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        atomicAdd(sync, 1u);
+        uint32_t seen, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync) : "memory");
+            if (seen < gridDim.x) {
+                __nanosleep(64);
+                if (++spins > (1u << 25)) __trap();   // seconds: the grid is not resident at once (or the workspace was not zero-filled)
+            }
+        } while (seen < gridDim.x);
+    }
+    __syncthreads();
+    {
+        const int rows = (int)gridDim.x, j = t & 15, k = t >> 4;   // NT_B = 288 -> k in 0..17
+        constexpr int SL = NT_B / 16;
+        for (int u = blockIdx.x; u * 16 < PTOTAL; u += rows) {
+            const int col = u * 16 + j;
+            float s = 0.f;
+            if (col < PTOTAL) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                int b = k;
+                for (; b + 3 * SL < rows; b += 4 * SL) {
+                    s0 += __ldcg(partials + (size_t)b * PTOTAL + col);
+                    s1 += __ldcg(partials + (size_t)(b + SL) * PTOTAL + col);
+                    s2 += __ldcg(partials + (size_t)(b + 2 * SL) * PTOTAL + col);
+                    s3 += __ldcg(partials + (size_t)(b + 3 * SL) * PTOTAL + col);
+                }
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;   // at most three left
+                if (b < rows) t0 = __ldcg(partials + (size_t)b * PTOTAL + col);
+                if (b + SL < rows) t1 = __ldcg(partials + (size_t)(b + SL) * PTOTAL + col);
+                if (b + 2 * SL < rows) t2 = __ldcg(partials + (size_t)(b + 2 * SL) * PTOTAL + col);
+                s = ((s0 + s1) + (s2 + s3)) + ((t0 + t1) + t2);
+            }
+            wred[k * 16 + j] = s;
+            __syncthreads();
+            if (t < 16 && col < PTOTAL) {
+                float tot = 0.f;
+#pragma unroll
+                for (int q = 0; q < SL; ++q) tot += wred[q * 16 + t];
+                float *dst = nullptr;
+                if (col < PW1) dst = gr.gW[0] ? gr.gW[0] + col : nullptr;
+                else if (col < PW2) dst = gr.gW[1] ? gr.gW[1] + (col - PW1) : nullptr;
+                else if (col < PW3) dst = gr.gW[2] ? gr.gW[2] + (col - PW2) : nullptr;
+                else if (col < PB0) dst = gr.gW[3] ? gr.gW[3] + (col - PW3) : nullptr;
+                else if (col < PB1) dst = gr.gb[0] ? gr.gb[0] + (col - PB0) : nullptr;
+                else if (col < PB2) dst = gr.gb[1] ? gr.gb[1] + (col - PB1) : nullptr;
+                else if (col < PB3) dst = gr.gb[2] ? gr.gb[2] + (col - PB2) : nullptr;
+                else if (col == PB3) dst = gr.gb[3];
+                if (dst) *dst += tot;
+            }
+            __syncthreads();
+        }
+    }
+    if (t == 0 && atomicAdd(sync + 1, 1u) == gridDim.x - 1) { sync[0] = 0u; sync[1] = 0u; }
 }
 
 bool tc_config_ok(const nafb_grid *grid, const nafb_mlp *mlp) {
@@ -933,21 +996,23 @@ int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerPa
 
 template <int SRC, int C>
 static int launch_bwd_tc_t(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, const float *dsig, float *grad_table,
-                           float *partials, const uint8_t *stash, long long *stamps, int grid, cudaStream_t s) {
+                           float *partials, const uint8_t *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_density_bwd_tc<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
         if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): %s", cudaGetErrorString(e));
         configured = true;
     }
-    k_density_bwd_tc<SRC, C><<<grid, NT_B, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, nafb_debug_flags());
+    // behind the partials: 4096 B of phase time stamps (debug), then the two words of the grid barrier
+    uint32_t *sync = gr.gW[0] || gr.gb[0] || gr.gW[1] ? reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(stamps) + 4096) : nullptr;
+    k_density_bwd_tc<SRC, C><<<grid, NT_B, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, nafb_debug_flags(), gr, sync);
     NAFB_CHECK_LAUNCH("density_backward(tc)");
     return NAFB_OK;
 }
 
 int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
-                       float *grad_table, float *partials, const void *stash, long long *stamps, int grid, cudaStream_t s) {
-#define CALL(S_, C_) launch_bwd_tc_t<S_, C_>(gp, mp, sp, P, dsig, grad_table, partials, (const uint8_t *)stash, stamps, grid, s)
+                       float *grad_table, float *partials, const void *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s) {
+#define CALL(S_, C_) launch_bwd_tc_t<S_, C_>(gp, mp, sp, P, dsig, grad_table, partials, (const uint8_t *)stash, stamps, grid, gr, s)
     switch (gp.C) {
         case 1: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 1) : CALL(NAFB_SRC_RAYS, 1);
         case 2: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 2) : CALL(NAFB_SRC_RAYS, 2);

@@ -1,13 +1,14 @@
 """NAFEngine -- the opt-in fused training / inference driver ("an opt-in
 fused train_step entry that bypasses autograd").
 
-One optimisation step is five kernel launches, captured once in a CUDA graph (nothing changes between replays: step
+One optimisation step is four kernel launches, captured once in a CUDA graph (nothing changes between replays: step
 count, learning rate and the sampler's RNG seed live in a device-resident state the kernels read and advance):
 
     density_forward (detector pixels or rays -> ray generation -> sampling -> gather -> MLP -> sum sigma*delta -> acc[N];
                      leaves the encodings in the stash)
     mse_loss        (masked chunk-wise MSE + d loss / d acc; clears acc)
-    density_backward(stash -> MLP forward/backward on tensor cores -> aggregated scatter into the flat gradient) + reduce_partials
+    density_backward(stash -> MLP forward/backward on tensor cores -> aggregated scatter into the flat gradient -> grid barrier ->
+                     reduction of the per-CTA MLP gradients)
     adam_step_dev   (fused dense Adam over ONE flat vector [table | MLP], zeroing the gradient) -- or, on several GPUs, the
                     fused exchange kernel (reduce-scatter + Adam + all-gather over NVLink peer memory)
 
@@ -393,8 +394,9 @@ class NAFEngine:
                 parallel.allreduce_sum_(self.flat_grad, self.pg)
         self._optimizer_kernel(par, timer)
 
-    # kernels of this library launched by one train_step (density_fwd, mse_loss, density_bwd, reduce_partials, adam / adam_exchange)
-    LAUNCHES_PER_STEP = 5
+    # kernels of this library launched by one train_step (density_fwd, mse_loss, density_bwd, adam / adam_exchange; the fp32 SIMT
+    # mode of the MLP adds a reduce_partials launch)
+    LAUNCHES_PER_STEP = 4
 
     def _load_inputs(self, s, rays, projs, mask, t_rand, pixels=None):
         """Inputs -> the static buffers the graph reads (device tensors, or pinned host tensors: one H2D copy each)."""

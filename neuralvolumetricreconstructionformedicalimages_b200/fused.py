@@ -62,7 +62,7 @@ def _workspace(mlp_struct, device):
     key = (device, n)
     ws = _ws_cache.get(key)
     if ws is None:
-        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        ws = torch.zeros(n, dtype=torch.uint8, device=device)   # zero-filled: it holds the words of the backward kernel's grid barrier
         _ws_cache[key] = ws
     return ws
 

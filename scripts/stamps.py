@@ -12,7 +12,7 @@ for i in range(3):
     eng.train_step(rays_b[i], projs_b[i], mask_b[i])
 torch.cuda.synchronize()
 ws = list(fused._ws_cache.values())[0]
-st = ws[-4096:].view(torch.int64).cpu().numpy().reshape(4, 128)
+st = ws[-4160:-64].view(torch.int64).cpu().numpy().reshape(4, 128)
 for c in range(4):
     s = st[c]
     n = int((s > 0).sum())

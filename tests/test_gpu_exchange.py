@@ -105,7 +105,7 @@ def test_engine_peer_mode_single_gpu_matches_default():
     pb, vb, lb = params[-1]
     for pa, va, la in params[:-1]:
         assert abs(la - lb) <= 1e-5 * abs(lb)
-        np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), rtol=0, atol=2e-5)     # 4 steps of lr 1e-3; float atomics order differs
+        np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), rtol=0, atol=5e-5)     # 4 steps of lr 1e-3; float atomics order differs (see _assert_same_parameters in test_gpu_parity.py)
         np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=1e-3, atol=1e-12)
 
 
@@ -160,5 +160,5 @@ def test_two_gpu_peer_exchange_matches_nccl(tmp_path):
     for mode in res:
         assert res[mode]["err"] == 0 and res[mode]["div"] == 0.0, mode    # no timed-out flag, replicas bit-identical
         if mode != "nccl":
-            np.testing.assert_allclose(res[mode]["param"].numpy(), res["nccl"]["param"].numpy(), rtol=0, atol=2e-5)
+            np.testing.assert_allclose(res[mode]["param"].numpy(), res["nccl"]["param"].numpy(), rtol=0, atol=5e-5)
             np.testing.assert_allclose(res[mode]["v"].numpy(), res["nccl"]["v"].numpy(), rtol=2e-3, atol=1e-12)
