@@ -458,7 +458,7 @@ def main():
                 else eng.train_step_host(projs_h[j], mask_h[j], rays=in_h[j]))
 
     for i in range(12):    # first use of a gradient parity runs eagerly, then one graph capture per (parity, staging slot)
-        step_host(i)
+        step_host(i % n_b)
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
