@@ -382,8 +382,9 @@ class NAFEngine:
                                              _lib.ptr(self.exp_avg_sq), self.n_params, self.betas[0], self.betas[1], self.eps,
                                              1.0 / self.world_size, 1, _lib.ptr(self.state), _lib.stream_ptr()))
 
-    def _whole_step(self, s, par, timer=None, t_rand=None, with_optimizer=True, use_pixels=False):
-        self._step_kernels(None if use_pixels else s["rays"], s["projs"], s["mask"], t_rand, s["loss"], s["dacc"], s["acc"], timer,
+    def _whole_step(self, s, par, timer=None, t_rand=None, with_optimizer=True, use_pixels=False, loss_out=None):
+        self._step_kernels(None if use_pixels else s["rays"], s["projs"], s["mask"], t_rand, s["loss"] if loss_out is None else loss_out,
+                           s["dacc"], s["acc"], timer,
                            stash=s["stash"], par=par, pixels=s["pixels"] if use_pixels else None)
         if with_optimizer:
             self._finish_step(par, timer)
@@ -489,8 +490,8 @@ class NAFEngine:
         """One optimisation step fed from HOST memory, result read back to the host: returns the loss as a python float.
 
         The end-to-end form of train_step: the inputs are copied into a pinned staging slot (a few KB of CPU memcpy), and
-        ONE graph launch performs the H2D copies, the whole iteration and the D2H copy of the loss into the slot; the call
-        then waits for the stream.  (train_step with pinned host tensors does the same with separate copy calls and leaves
+        ONE graph launch performs the H2D copy and the whole iteration, whose loss kernel writes the result straight into the
+        slot's pinned host buffer (zero-copy D2H); the call then waits for the stream.  (train_step with pinned host tensors does the same with separate copy calls and leaves
         the loss on the device.)
 
         wait=False returns a PendingLoss instead of waiting: `.result()` gives the float once the step has run.  The staging
@@ -528,9 +529,9 @@ class NAFEngine:
                 else:
                     s["packed"][o_rays:o_rays + 32 * N].copy_(h["packed"][o_rays:o_rays + 32 * N], non_blocking=True)
                     s["packed"][o_projs:end].copy_(h["packed"][o_projs:end], non_blocking=True)
-                self._whole_step(s, par, None, None, with_optimizer=with_optimizer, use_pixels=use_pixels)
-                if with_optimizer:
-                    h["loss"].copy_(s["loss"], non_blocking=True)
+                # the loss kernel stores its two floats straight into the slot's pinned (device-mapped) host buffer: no D2H copy
+                # node at the end of the graph, and the PCIe write is long done when the backward pass and the optimizer retire
+                self._whole_step(s, par, None, None, with_optimizer=with_optimizer, use_pixels=use_pixels, loss_out=h["loss"])
 
             shape_key = (N, mask is not None, par, "host", use_pixels)
             key = shape_key + (slot,)
@@ -547,7 +548,6 @@ class NAFEngine:
                 g.replay()
                 if not in_graph:
                     self._finish_step(par)
-                    h["loss"].copy_(s["loss"], non_blocking=True)
             self.step_count += 1
             h["event"].record()
         h["pending"] = PendingLoss(h["event"], h["loss"])
