@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(NT_B, 2) k_density_bwd_tc(const GridParams gp,
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync) : "memory");
             if (seen < gridDim.x) {
                 __nanosleep(64);
-                if (++spins > (1u << 22)) __trap();   // seconds: the grid is not resident at once (or the workspace was not zero-filled)
+                if (++spins > (1u << 24)) __trap();   // seconds: the grid is not resident at once (or the workspace was not zero-filled)
             }
         } while (seen < gridDim.x);
     }
