@@ -176,6 +176,15 @@ class PeerExchange:
                 b.release()
 
 
+def _stage(dst: torch.Tensor, src: torch.Tensor, dtype):
+    """src -> dst (a view of a pinned staging buffer).  dtype None: any 1-byte type (uint8 / bool masks)."""
+    if (src.device.type == "cpu" and src.is_contiguous() and src.numel() == dst.numel()
+            and (src.dtype == dtype or (dtype is None and src.element_size() == 1))):
+        ctypes.memmove(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size())
+    else:
+        dst.copy_(src.reshape(dst.shape))
+
+
 class PendingLoss:
     """The loss of a step enqueued by NAFEngine.train_step_host(wait=False): `result()` waits for that step and returns the float."""
     __slots__ = ("_event", "_buf", "_value")
@@ -507,17 +516,20 @@ class NAFEngine:
         hk = ("host_pix" if use_pixels else "host_rays", slot)
         if s.get(hk) is None:
             hp = torch.zeros(s["packed"].numel(), dtype=torch.uint8).pin_memory()      # host mirror of the packed input buffer
+            loss = torch.zeros(2, dtype=torch.float32).pin_memory()
             s[hk] = dict(packed=hp, inp=(hp[o_pix:o_pix + 12 * N].view(torch.int32).view(N, 3) if use_pixels
                                          else hp[o_rays:o_rays + 32 * N].view(torch.float32).view(N, 8)),
                          projs=hp[o_projs:o_projs + 4 * N].view(torch.float32), mask=hp[o_mask:o_mask + N],
-                         loss=torch.zeros(2, dtype=torch.float32).pin_memory(), event=torch.cuda.Event(), pending=None)
+                         loss=loss, loss_np=loss.numpy(), event=torch.cuda.Event(), pending=None)
         h = s[hk]
         if h["pending"] is not None:
             h["pending"].result()      # the launch that last used this slot has read its inputs and written its loss
-        h["inp"].copy_(src.reshape(h["inp"].shape))
-        h["projs"].copy_(projs.reshape(N))
+        # staging: a few KB; plain memmove when the caller's tensors already have the staged layout (a torch copy_ call costs
+        # more than the copy itself at this size, and in the waited form every host microsecond is on the critical path)
+        _stage(h["inp"], src, torch.int32 if use_pixels else torch.float32)
+        _stage(h["projs"], projs, torch.float32)
         if mask is not None:
-            h["mask"].copy_(mask.reshape(N))
+            _stage(h["mask"], mask, None)
         end = o_mask + N if mask is not None else o_projs + 4 * N
         with torch.cuda.device(self.device):
             par = self._parity()
@@ -550,7 +562,7 @@ class NAFEngine:
                     self._finish_step(par)
             self.step_count += 1
             h["event"].record()
-        h["pending"] = PendingLoss(h["event"], h["loss"])
+        h["pending"] = PendingLoss(h["event"], h["loss_np"])
         return h["pending"].result() if wait else h["pending"]
 
     # ------------------------------------------------------------------ inference

@@ -493,15 +493,16 @@ def test_density_ragged_and_range(mlp_mode):
         net(torch.full((3, 3), 0.31, device=DEV))
     assert net(torch.zeros(4, 5, 3, device=DEV)).shape == (4, 5, 1)
 
-def _assert_same_parameters(a, b, what):
-    """Two runs of the same optimisation steps agree up to the order of the float atomics (ray sums, table gradients): a last-bit
-    difference in a gradient entry whose summands nearly cancel is a relative difference of up to ~1e-2 of that entry, and Adam's
-    per-entry normalisation turns it into ~1e-2 of one learning-rate step (1e-3): so all but a handful of the 14 M parameters agree
-    to 5e-6, and every one to 5e-5."""
+def _assert_same_parameters(a, b, what, steps=3):
+    """Two runs of the same `steps` optimisation steps agree up to the order of the float atomics (ray sums, table gradients): a
+    last-bit difference in a gradient entry whose summands nearly cancel is a relative difference of up to ~1e-2 of that entry, and
+    Adam's per-entry normalisation turns it into ~1e-2 of one learning-rate step (1e-3) -- per step, and it accumulates: all but a
+    handful of the 14 M parameters agree to 5e-6 (observed: 26 after 3 steps, 84 after 11), every one to 2e-5 per step taken
+    (observed 1.4e-5 after 3 steps, 5.3e-5 after 11)."""
     a, b = a.detach().cpu().numpy(), b.detach().cpu().numpy()
     d = np.abs(a - b)
     bad = np.flatnonzero(d > 5e-6)
-    assert d.max() <= 5e-5 and bad.size <= 1e-5 * a.size, \
+    assert d.max() <= 2e-5 * steps and bad.size <= 1e-5 * a.size * max(1, steps // 3), \
         f"{what}: {bad.size} of {a.size} parameters differ by more than 5e-6 (max {d.max():.3e}), flat indices {bad[:20]}"
 
 
@@ -558,7 +559,7 @@ def test_engine_pixel_batches_equal_ray_batches():
             loss = eng.train_step(None if use_pixels else rays, projs, None, t_rand, pixels=pixels if use_pixels else None)
         res.append((float(loss.item()), eng.flat_param.clone()))
     assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
-    _assert_same_parameters(res[0][1], res[1][1], "pixel batch vs ray batch")
+    _assert_same_parameters(res[0][1], res[1][1], "pixel batch vs ray batch", steps=2)
     # the host entry (pinned staging + one graph launch incl. H2D / D2H) performs the same steps
     torch.manual_seed(0)
     net = _chest_net(table_scale=0.3)
@@ -571,7 +572,7 @@ def test_engine_pixel_batches_equal_ray_batches():
         lh = eng.train_step_host(projs.cpu(), None, pixels=pixels.cpu())
         ld = eng2.train_step(None, projs, None, pixels=pixels)
     assert isinstance(lh, float) and abs(lh - float(ld.item())) <= 1e-5 * abs(lh)
-    _assert_same_parameters(eng.flat_param, eng2.flat_param, "host entry vs device entry")
+    _assert_same_parameters(eng.flat_param, eng2.flat_param, "host entry vs device entry", steps=3)
     # pipelined form: steps enqueued without waiting (rotating staging slots, different inputs per step so that a slot overwritten
     # too early would show), losses collected afterwards == the same steps one by one
     batches = [(torch.from_numpy(rng.uniform(0, 0.05, N).astype(np.float32)), torch.from_numpy(np.roll(pix, k + 1, axis=0).copy())) for k in range(8)]
@@ -580,7 +581,7 @@ def test_engine_pixel_batches_equal_ray_batches():
     got = [p_.result() for p_ in pending]
     assert all(p_.done() for p_ in pending)
     np.testing.assert_allclose(got, sync, rtol=1e-5)
-    _assert_same_parameters(eng.flat_param, eng2.flat_param, "pipelined host entry vs device entry")
+    _assert_same_parameters(eng.flat_param, eng2.flat_param, "pipelined host entry vs device entry", steps=11)
 
 
 # ----------------------------------------------------------------------------- render
