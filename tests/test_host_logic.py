@@ -231,3 +231,44 @@ def test_phantom_pickle_schema_roundtrip_and_reference_loader(tmp_path):
     ds = mod.TIGREDataset(path, n_rays=32, type="train", device="cpu")
     assert np.array_equal(ds.rays.numpy().view(np.uint32), ours.numpy().view(np.uint32))
     assert np.array_equal(ds.projs.numpy(), back["train"]["projections"])
+
+
+def test_host_staging_and_pending_loss_logic():
+    """Host-side pieces of NAFEngine.train_step_host that need no GPU: the staging copy (memmove fast path and the converting
+    fallback) and the PendingLoss handle (waits once, caches the value, survives the reuse of its slot)."""
+    import numpy as np
+    import torch
+    from neuralvolumetricreconstructionformedicalimages_b200.engine import PendingLoss, _stage
+
+    buf = torch.zeros(64, dtype=torch.uint8)
+    pix = buf[:48].view(torch.int32).view(4, 3)
+    src = torch.arange(12, dtype=torch.int32).view(4, 3)
+    _stage(pix, src, torch.int32)                         # same layout: memmove
+    assert torch.equal(pix, src)
+    _stage(pix, (src + 100).to(torch.int64), torch.int32)  # other dtype: converting copy
+    assert torch.equal(pix, src + 100)
+    _stage(pix, (src + 7).t().contiguous().t(), torch.int32)   # non-contiguous view: copy_ keeps the logical order
+    assert torch.equal(pix, src + 7)
+    m = buf[48:52]
+    _stage(m, torch.tensor([True, False, True, True]), None)   # bool mask into the uint8 staging bytes
+    assert m.tolist() == [1, 0, 1, 1]
+    _stage(m, torch.tensor([0, 1, 0, 1], dtype=torch.uint8), None)
+    assert m.tolist() == [0, 1, 0, 1]
+
+    class FakeEvent:
+        def __init__(self):
+            self.synced, self.ready = 0, False
+
+        def query(self):
+            return self.ready
+
+        def synchronize(self):
+            self.synced += 1
+            self.ready = True
+
+    ev, loss = FakeEvent(), np.array([0.25, 3.0], dtype=np.float32)
+    p = PendingLoss(ev, loss)
+    assert not p.done()
+    assert p.result() == 0.25 and ev.synced == 1 and p.done()
+    loss[0] = 9.0                                          # the slot is reused by a later step
+    assert p.result() == 0.25 and ev.synced == 1           # cached: no second wait, no stale read
