@@ -2,7 +2,8 @@
 Python half of the NAF hot path.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 Reference files restated (paths relative to /root/reference):
-  src/render/render.py        sampling :88-105, raw2outputs :178-212, render :31-146, run_network :148-156
+  src/render/render.py        sampling :88-105, raw2outputs :178-212, render :31-146, run_network :148-156,
+                              hierarchical pass :113-126, sample_pdf :215-247, raw_noise_std :196-199
   src/network/network.py      DensityNetwork :5-58
   src/encoder/freqencoder.py  FreqEncoder :29-43
   src/loss/loss.py            calc_mse_loss :26-46
@@ -80,6 +81,54 @@ def ray_integral(raw: torch.Tensor, z_vals: torch.Tensor, rays_d: torch.Tensor):
     else:
         raise NotImplementedError("Wrong raw shape")
     return acc, w
+
+
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, det: bool) -> torch.Tensor:
+    """render.py:215-247: inverse-CDF sampling of the fine pass.  bins [N,B], weights [N,B-1] -> [N,n_samples].
+    det: u = linspace(0,1); else u is drawn from torch's GLOBAL CPU generator, as the reference does."""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    shape = list(cdf.shape[:-1]) + [n_samples]
+    u = torch.linspace(0., 1., steps=n_samples).expand(shape) if det else torch.rand(shape)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
+    cdf_lo, cdf_hi = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+    bin_lo, bin_hi = torch.gather(bins, -1, below), torch.gather(bins, -1, above)
+    denom = cdf_hi - cdf_lo
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    return bin_lo + (u - cdf_lo) / denom * (bin_hi - bin_lo)
+
+
+def ray_integral_noisy(raw, z_vals, rays_d, raw_noise_std):
+    """render.py:192-212 with raw_noise_std > 0: the noise (global CPU generator) enters the line integral only, the weights are
+    taken from the un-noised prediction."""
+    noise = torch.randn(raw[..., 0].shape) * raw_noise_std if raw_noise_std > 0. else None
+    acc, w = ray_integral(raw, z_vals, rays_d)
+    if noise is not None:
+        noisy = torch.cat([raw[..., :1] + noise[..., None], raw[..., 1:]], -1)
+        acc, _ = ray_integral(noisy, z_vals, rays_d)
+    return acc, w
+
+
+def render_hierarchical(rays, net, net_fine, n_samples, n_fine, perturb, raw_noise_std=0., netchunk=409600):
+    """render.py:82-146 with a fine network (n_fine > 0), single chunk.  Random draws come from torch's global generators in the
+    reference's order: t_rand (:99), coarse noise (:197), u of sample_pdf (:226), fine noise (:197)."""
+    t_rand = torch.rand([rays.shape[0], n_samples]) if perturb else None
+    z, pts = sample_points(rays, n_samples, bool(perturb), t_rand, net.bound)
+    raw = run_network(pts, net, netchunk)
+    acc0, w0 = ray_integral_noisy(raw, z, rays[:, 3:6], raw_noise_std)
+    z_mid = .5 * (z[:, 1:] + z[:, :-1])
+    z_samples = sample_pdf(z_mid, w0[:, 1:-1], n_fine, det=(perturb == 0.)).detach()
+    z_all, _ = torch.sort(torch.cat([z, z_samples], -1), -1)
+    b = net.bound - 1e-6
+    pts_all = (rays[:, None, 0:3] + rays[:, None, 3:6] * z_all[:, :, None]).clamp(-b, b)
+    raw_f = run_network(pts_all, net_fine, netchunk)
+    acc, _ = ray_integral_noisy(raw_f, z_all, rays[:, 3:6], raw_noise_std)
+    return {"acc": acc, "pts": pts_all, "tv_loss": tv_of_points(pts_all), "acc0": acc0, "weights0": w0, "pts0": pts}
 
 
 def tv_of_points(pts: torch.Tensor) -> torch.Tensor:

@@ -266,6 +266,35 @@ def gen_geometry_fixtures():
     np.savez_compressed(os.path.join(HERE, "geometry.npz"), **out)
 
 
+def gen_fine_fixtures():
+    """render() with a fine network (n_fine > 0), raw_noise_std > 0 and a two-channel coarse head (render.py:113-126, :196-199,
+    :207-208, sample_pdf :215-247) on the frequency-encoder network: inputs, generator seed and the reference's outputs."""
+    import src.render  # noqa: F401
+    rr = sys.modules["src.render.render"]
+    from src.encoder import get_encoder
+    from src.network import get_network
+
+    rng = np.random.default_rng(17)
+    N, S, NF = 24, 16, 8
+    rays = torch.from_numpy(make_rays(N, rng))
+    out = dict(rays=rays.numpy(), n_samples=S, n_fine=NF, seed=123)
+    enc = get_encoder("frequency", multires=6)
+    fine = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid")
+    _seed_mlp(fine, 12)
+    out.update(_mlp_arrays(fine, "fine_"))
+    for out_dim in (1, 2):
+        net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=out_dim, last_activation="sigmoid")
+        _seed_mlp(net, 10 + out_dim)
+        out.update(_mlp_arrays(net, f"coarse{out_dim}_"))
+        for perturb, noise in ((False, 0.0), (True, 0.0), (True, 0.3)):
+            torch.manual_seed(123)
+            ret = rr.render(rays, net, fine, S, NF, perturb, 409600, noise)
+            tag = f"od{out_dim}_p{int(perturb)}_n{int(noise > 0)}_"
+            for k in ("acc", "pts", "tv_loss", "acc0", "weights0", "pts0"):
+                out[tag + k] = ret[k].detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "render_fine.npz"), **out)
+
+
 def gen_signatures():
     """The operator-API surface the drop-in must mirror (names, order, defaults)."""
     import inspect
@@ -302,9 +331,14 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     oh.build_oracle()
     oh.build_ref()
+    if sys.argv[1:] == ["fine"]:      # only the hierarchical-sampling fixture (added later; the others stay as committed)
+        install_reference()
+        gen_fine_fixtures()
+        sys.exit(0)
     gen_hash_fixtures()
     install_reference()
     gen_render_fixtures()
+    gen_fine_fixtures()
     gen_geometry_fixtures()
     gen_signatures()
     for f in sorted(os.listdir(HERE)):

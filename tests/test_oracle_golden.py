@@ -107,6 +107,34 @@ def test_render_freq(golden):
     np.testing.assert_allclose(r1["tv_loss"].numpy(), fx["freq_tv_perturb"], rtol=1e-5)
 
 
+def test_render_hierarchical_noise_two_channel(golden):
+    """The oracle's restatement of the fine pass (render.py:113-126, sample_pdf :215-247), of raw_noise_std (:196-199) and of the
+    two-channel weights (:207-208) against outputs of the reference's own render() (tests/golden/generate_golden.py fine), the
+    random draws reproduced from the same generator seed in the reference's order."""
+    fx = golden("render_fine.npz")
+    S, NF = int(fx["n_samples"]), int(fx["n_fine"])
+    rays = torch.from_numpy(fx["rays"])
+    fine = naf.OracleDensityNetwork(naf.OracleFreqEncoder(3, 6), bound=0.3, num_layers=4, hidden_dim=32, skips=[2])
+    _load_mlp(fine, fx, "fine_")
+    for out_dim in (1, 2):
+        net = naf.OracleDensityNetwork(naf.OracleFreqEncoder(3, 6), bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=out_dim)
+        _load_mlp(net, fx, f"coarse{out_dim}_")
+        for perturb, noise in ((False, 0.0), (True, 0.0), (True, 0.3)):
+            tag = f"od{out_dim}_p{int(perturb)}_n{int(noise > 0)}_"
+            torch.manual_seed(int(fx["seed"]))
+            with torch.no_grad():
+                r = naf.render_hierarchical(rays, net, fine, S, NF, perturb, noise)
+            assert np.array_equal(r["pts0"].numpy().view(np.uint32), fx[tag + "pts0"].view(np.uint32)), tag
+            np.testing.assert_allclose(r["acc0"].numpy(), fx[tag + "acc0"], rtol=2e-6, atol=1e-8, err_msg=tag)
+            np.testing.assert_allclose(r["weights0"].numpy(), fx[tag + "weights0"], rtol=1e-5, atol=1e-7, err_msg=tag)
+            # same torch-CPU ops on the same values: the fine positions agree to the last bits of the CDF arithmetic
+            np.testing.assert_allclose(r["pts"].numpy(), fx[tag + "pts"], rtol=0, atol=2e-7, err_msg=tag)
+            np.testing.assert_allclose(r["acc"].numpy(), fx[tag + "acc"], rtol=5e-6, atol=1e-8, err_msg=tag)
+            np.testing.assert_allclose(float(r["tv_loss"]), float(fx[tag + "tv_loss"]), rtol=1e-5, err_msg=tag)
+    # the noise changes the integral but not the weights (it is added inside the sum only)
+    assert np.array_equal(fx["od1_p1_n0_weights0"], fx["od1_p1_n1_weights0"]) and not np.allclose(fx["od1_p1_n0_acc0"], fx["od1_p1_n1_acc0"])
+
+
 def _chest_net(fx, table_scale=0.5, **kw):
     enc = oh.OracleHashEncoder(3, 16, 2, 16, 19, use_ref=False, normalise="mul_recip")  # as the fixtures (CUDA evaluation)
     with torch.no_grad():
