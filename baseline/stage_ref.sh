@@ -15,6 +15,9 @@ mkdir -p "$OUT"
 rm -rf "$OUT/src"
 cp -r "$REF_ROOT/src" "$OUT/src"
 cp "$REF_ROOT/train.py" "$OUT/train.py"
+# the shipped YAMLs and the lamino angle grid: tests/test_gpu_trainer.py drives the UNMODIFIED src/trainer.py with them
+rm -rf "$OUT/config" && cp -r "$REF_ROOT/config" "$OUT/config"
+mkdir -p "$OUT/data" && cp "$REF_ROOT/data/angles_real.npy" "$OUT/data/angles_real.npy"
 CU="$OUT/src/encoder/hashencoder/src/hashencoder.cu"
 sed -i 's/inputs\.type()/inputs.scalar_type()/; s/grad\.type()/grad.scalar_type()/' "$CU"
 grep -n "scalar_type()" "$CU"

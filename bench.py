@@ -522,6 +522,7 @@ def main():
         STASH = 128
         algo = {
             "density_fwd": (FLOP_FWD_PER_POINT * pts_step, (TABLE_BYTES_PER_POINT + STASH) * pts_step),
+            "density_fwd_loss": (FLOP_FWD_PER_POINT * pts_step, (TABLE_BYTES_PER_POINT + STASH) * pts_step),
             "density_bwd": (FLOP_FWDBWD_PER_POINT * pts_step, (TABLE_BYTES_PER_POINT + STASH) * pts_step),
             "adam": (0, 32 * eng.n_params),
             # peer exchange: per rank 4 B/param zeroed + its 1/W slice: W gradient reads, p/m/v read+write, W parameter writes
@@ -535,9 +536,10 @@ def main():
             kernels[name] = k
         # gather / reduction operation rates against the measured L2-resident rates (scripts/microbench.py):
         # these, not bytes, are what bound the encoder on this machine
-        if "density_fwd" in kernels:
-            kernels["density_fwd"]["gather_gops"] = 128 * pts_step / (kernels["density_fwd"]["ms"] * 1e-3) / 1e9
-            kernels["density_fwd"]["gather_gops_measured_peak"] = 263.5
+        for fk in ("density_fwd", "density_fwd_loss"):
+            if fk in kernels:
+                kernels[fk]["gather_gops"] = 128 * pts_step / (kernels[fk]["ms"] * 1e-3) / 1e9
+                kernels[fk]["gather_gops_measured_peak"] = 263.5
         if "density_bwd" in kernels:
             kernels["density_bwd"]["reduction_gops"] = 128 * pts_step / (kernels["density_bwd"]["ms"] * 1e-3) / 1e9
             kernels["density_bwd"]["reduction_gops_measured_peak"] = 184.0
@@ -576,7 +578,7 @@ def main():
                     "pipelined": {"value": world * pts_step * K / (piped_wall_ms * 1e-3), "unit": "samples/s", "ms_per_step": piped_wall_ms / K,
                                   "note": "train_step_host(wait=False): the loss of step k is read after step k+1 has been enqueued; "
                                           "same H2D / D2H bytes every step"}},
-            "gpu_launches": eng.LAUNCHES_PER_STEP * K,
+            "gpu_launches": eng.launches_per_step * K,
             "roofline": roofline,
             "kernels": kernels,
             "final_loss": final_loss, "host_loss": host_loss, "host_loss_pipelined": piped_loss,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 8
+#define NAFB_ABI_VERSION 9
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -99,9 +99,17 @@ typedef struct nafb_mlp {
     uint32_t out_dim;                   /* 1 */
     uint32_t skip_mask;                 /* bit i set <=> layer i takes cat([enc, h]) */
     uint32_t head;                      /* enum nafb_activation */
+    uint32_t arith;                     /* enum nafb_arith: how the fused density kernels evaluate the layers (per call; the
+                                           library keeps no mode of its own) */
     const float *W[NAFB_MAX_LAYERS];    /* device, nn.Linear weight [out, in] row-major */
     const float *b[NAFB_MAX_LAYERS];    /* device, [out] */
 } nafb_mlp;
+
+/* Arithmetic of the fused density kernels (nafb_mlp.arith):
+ *   NAFB_ARITH_TC   tcgen05 tensor cores with bf16x3 split operands (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM)
+ *                   wherever the configuration allows (L*C == 32, 4 x 32 MLP, skip at 2, out_dim 1); other shapes run SIMT;
+ *   NAFB_ARITH_SIMT fp32 FMAs everywhere (bit-reproducible dot-product order; the general-shape path). */
+enum nafb_arith { NAFB_ARITH_TC = 0, NAFB_ARITH_SIMT = 1 };
 
 typedef struct nafb_mlp_grads {
     float *gW[NAFB_MAX_LAYERS]; /* device, same shapes as W; ACCUMULATED into */
@@ -120,8 +128,10 @@ enum nafb_point_source {
 #define NAFB_STATE_STEP 0     /* completed optimizer steps (incremented by nafb_adam_step_dev / nafb_adam_exchange_step) */
 #define NAFB_STATE_SEED_LO 1  /* seed of the in-kernel sampler generator */
 #define NAFB_STATE_SEED_HI 2
-#define NAFB_STATE_LR 3       /* learning rate (float bits) */
-#define NAFB_STATE_TICKET 4   /* internal (zero between launches) */
+#define NAFB_STATE_LR 6       /* learning rate: the bits of a DOUBLE in words 6 (low) and 7 (high) -- torch.optim.Adam evaluates
+                                 lr / (1 - beta1^t) in python floats, i.e. doubles; a float would change the last bit of the step */
+#define NAFB_STATE_TICKET 4   /* internal (zero between launches): last-block detection of the optimizer kernels */
+#define NAFB_STATE_TICKET_FWD 5 /* internal (zero between launches): a word the engine hands nafb_loss_tail.ticket */
 #define NAFB_STATE_WORDS 8
 
 typedef struct nafb_sampler {
@@ -174,6 +184,24 @@ int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_
                          float *sigma, float *acc, float *z_vals, float *pts_out, int32_t *flags,
                          void *stash, nafb_stream_t stream);
 
+/* Training forward of one ray batch WITH the loss in the same launch (train.py:69-127 after render.py:31): as
+ * nafb_density_forward(src = NAFB_SRC_RAYS, sigma = z_vals = pts_out = NULL), and the LAST CTA of the kernel to retire
+ * evaluates nafb_mse_loss(acc, target, mask, n_rays, chunk, gscale, loss_out, dacc, zero_pred) -- the step needs no
+ * separate loss launch.  `ticket`: one device word, zero before the first use (the kernel leaves it zero).
+ * Tensor-core configurations only (NAFB_ERR_UNSUPPORTED otherwise: launch nafb_density_forward + nafb_mse_loss). */
+typedef struct nafb_loss_tail {
+    const float *target;   /* [n_rays] measured projections                                   */
+    const uint8_t *mask;   /* [n_rays] or NULL                                                */
+    uint32_t chunk;        /* 0: one chunk                                                    */
+    float gscale;
+    float *loss_out;       /* [2]: loss, number of valid rays (device or device-mapped host)  */
+    float *dacc;           /* [n_rays] d loss / d acc                                         */
+    int32_t zero_pred;     /* as in nafb_mse_loss                                             */
+    uint32_t *ticket;
+} nafb_loss_tail;
+int nafb_density_forward_loss(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, float *acc,
+                              int32_t *flags, void *stash, const nafb_loss_tail *loss, nafb_stream_t stream);
+
 /* Backward of the above.  dsigma [P] (src POINTS) or dacc [N] (src RAYS: dsigma is derived as
  * dacc[r] * delta[r,i] in-kernel).  Recomputes the forward activations from the points (and the
  * stash, when given), accumulates MLP gradients and scatters into grad_table.
@@ -211,12 +239,38 @@ int nafb_ray_integral_backward(const float *dacc, uint32_t out_dim, const float 
 int nafb_mse_loss(float *pred, const float *target, const uint8_t *mask, uint32_t n, uint32_t chunk,
                   float gscale, float *loss_out, float *dpred, int zero_pred, nafb_stream_t stream);
 
+/* ------------------------------------------------------------------ per-iteration dataset work on the device
+ * nafb_ptycho_mask: get_ptycho_mask (reference src/utils/util.py:196-205; train.py:59-60 recomputes it every iteration) for a
+ * whole scan at once: full_proj [n_proj, H, W] complex64 (interleaved re, im), keep [n_proj, H, W] = 1 where the pixel is kept. */
+int nafb_ptycho_mask(const float *full_proj, uint32_t n_proj, uint32_t H, uint32_t W, float threshold, uint8_t *keep,
+                     nafb_stream_t stream);
+
+/* nafb_draw_pixels: TIGREDataset.__getitem__ (reference src/dataset/tigre.py:354-382) -- n_rays of the non-zero pixels of ONE
+ * projection, uniformly without replacement and in random order (np.random.choice(replace=False), :358), their projection
+ * values (:364) and mask bits (train.py:93-95), written where the fused training step reads its batch.
+ *   valid [n_proj, H*W]: per projection the flat indices (row * W + col) of its non-zero pixels, front-packed; n_valid [n_proj];
+ *   order: projection of draw k = order[k % n_order] (NULL: k % n_proj, the order of the reference's un-shuffled DataLoader);
+ *   draw_state [4] (device): draw counter (incremented by the launch), seed lo, seed hi, error word (1 + projection when a
+ *   projection has fewer than n_rays valid pixels -- the reference's np.random.choice raises there).
+ * No argument changes between launches: the draw can sit in the CUDA graph of the training step.  n_rays <= 8192. */
+typedef struct nafb_pixel_source {
+    const float *projs;      /* [n_proj, H, W] */
+    const uint8_t *mask;     /* [n_proj, H, W] keep-mask, or NULL (all kept) */
+    const int32_t *valid;
+    const int32_t *n_valid;
+    const int32_t *order;
+    uint32_t n_proj, H, W, n_order;
+} nafb_pixel_source;
+int nafb_draw_pixels(const nafb_pixel_source *src, uint32_t n_rays, int32_t *pixels_out, float *projs_out, uint8_t *mask_out,
+                     uint32_t *draw_state, nafb_stream_t stream);
+
 /* ------------------------------------------------------------------ optimiser
  * torch.optim.Adam (trainer.py:54: betas (0.9,0.999), eps 1e-8, no weight decay, no amsgrad),
  * one fused pass over a flat parameter vector; grad is zeroed in the same pass when zero_grad != 0
- * (trainer.py:138 optimizer.zero_grad()).  `step` is the 1-based step count. */
-int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float lr,
-                   float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad,
+ * (trainer.py:138 optimizer.zero_grad()).  `step` is the 1-based step count.  The hyper-parameters are DOUBLES, like the python
+ * floats torch.optim.Adam computes its scalar constants from: with them the update is bit-identical to torch's (tested). */
+int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, double lr,
+                   double beta1, double beta2, double eps, uint32_t step, float grad_scale, int zero_grad,
                    nafb_stream_t stream);
 
 /* ------------------------------------------------------------------ multi-GPU exchange step
@@ -249,7 +303,7 @@ typedef struct nafb_exchange {
     float *exp_avg, *exp_avg_sq;       /* LOCAL, slice-sized: [i1 - i0] of nafb_exchange_slice(n, rank, world)  */
     uint64_t n;                        /* floats, multiple of 4                                                 */
     uint32_t *state;                   /* optional device nafb_step_state: when non-NULL the epoch is state[0] + 1 and
-                                          the learning rate state[3] (the `step` / `lr` arguments are ignored), and
+                                          the learning rate the double in state[6..7] (the `step` / `lr` arguments are ignored), and
                                           the kernel increments state[0]: the launch can sit in a replayed CUDA graph */
     float *mc_param;                   /* optional NVLS (NVLink SHARP) multicast address of the parameter vector ...    */
     const float *mc_grad;              /* ... and of this step's gradient: the slice sum is then one multimem.ld_reduce
@@ -271,36 +325,14 @@ int nafb_peer_close(void *ptr);
 int nafb_peer_free(void *ptr);
 /* [i0, i1) in floats (multiples of 4) of the slice rank `rank` owns */
 int nafb_exchange_slice(uint64_t n, uint32_t rank, uint32_t world, uint64_t *i0, uint64_t *i1);
-int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float beta2, float eps, uint32_t step,
+int nafb_adam_exchange_step(const nafb_exchange *x, double lr, double beta1, double beta2, double eps, uint32_t step,
                             float grad_scale, nafb_stream_t stream);
 
 /* Same optimizer step with the step count and learning rate taken from a device nafb_step_state: (the bias corrections
  * are evaluated on the device in double precision, as torch does on the host); state[0] is incremented when the last
  * block retires.  Graph-capturable: no argument changes from step to step. */
-int nafb_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float beta1, float beta2,
-                       float eps, float grad_scale, int zero_grad, uint32_t *state, nafb_stream_t stream);
-
-/* Arithmetic of the fused density kernels: 0 (default) = tcgen05 tensor cores with bf16x3 split
- * operands and fp32 TMEM accumulation wherever the configuration allows (4 x 32 MLP, skip at 2),
- * 1 = fp32 SIMT FMAs everywhere (bit-reproducible dot-product order; the general-shape path),
- * 2 = as 0 with the warp-specialised forward kernel (producer warps gather the next tile while the
- *     epilogue warps run the MLP chain of the current one; measured slower than 0 at chest_50, kept
- *     selectable: see DESIGN.md section 4.2). */
-int nafb_set_mlp_mode(int mode);
-
-/* ------------------------------------------------------------------ diagnostics
- * Known-answer test of the tcgen05 plumbing (one 128-row tile, bf16x3 split precision):
- *   D1 [128,32] = A[:, :32] . W[:, :32]^T ; D2 [128,64] = A[:, :32] . W ; D3 [128,32] = A^T . X
- * with A [128,128], X [128,32], W [32,64] fp32 row-major. */
-/* Random-access microbenchmarks over a device buffer of n_floats floats (measured denominators of the
- * L2 gather / scatter roofline): mode 0/1/2 = ld.f32/.v2/.v4, 3/4/5 = red.add .f32/.v2/.v4,
- * 6 = red.v2 warp-uniform address, 7 = red.v2 lane pairs on one address, 8 = two adjacent ld.v2.
- * Enqueues one kernel; *h_ops receives the number of operations it performs. */
-int nafb_microbench(int mode, float *buf, uint32_t n_floats, int iters, float *sink, uint64_t *h_ops,
-                    nafb_stream_t stream);
-
-int nafb_selftest_umma(const float *A, const float *X, const float *W, float *D1, float *D2, float *D3,
-                       nafb_stream_t stream);
+int nafb_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, double beta1, double beta2,
+                       double eps, float grad_scale, int zero_grad, uint32_t *state, nafb_stream_t stream);
 
 #ifdef __cplusplus
 }

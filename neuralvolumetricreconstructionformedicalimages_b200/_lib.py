@@ -15,14 +15,16 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnafb200.so")
+DIAG_LIB_PATH = os.path.join(_HERE, "libnafb200_diag.so")   # diagnostics (tests / scripts only): include/nafb200_diag.h
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 NAFB_MAX_LEVELS = 32
 NAFB_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 ACT = {"sigmoid": 0, "relu": 1, "tanh": 2, "none": 3}
 LAYOUT_LBC, LAYOUT_BLC = 0, 1
 SRC_POINTS, SRC_RAYS, SRC_VOXELS = 0, 1, 2
+ARITH_TC, ARITH_SIMT = 0, 1          # enum nafb_arith (nafb_mlp.arith)
 
 c_f32p = ctypes.c_void_p
 u32, u64, i32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int32
@@ -33,8 +35,18 @@ class Grid(ctypes.Structure):
 
 
 class Mlp(ctypes.Structure):
-    _fields_ = [("n_layers", u32), ("in_dim", u32), ("hidden", u32), ("out_dim", u32), ("skip_mask", u32), ("head", u32),
+    _fields_ = [("n_layers", u32), ("in_dim", u32), ("hidden", u32), ("out_dim", u32), ("skip_mask", u32), ("head", u32), ("arith", u32),
                 ("W", ctypes.c_void_p * NAFB_MAX_LAYERS), ("b", ctypes.c_void_p * NAFB_MAX_LAYERS)]
+
+
+class LossTail(ctypes.Structure):
+    _fields_ = [("target", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("chunk", u32), ("gscale", ctypes.c_float), ("loss_out", ctypes.c_void_p),
+                ("dacc", ctypes.c_void_p), ("zero_pred", i32), ("ticket", ctypes.c_void_p)]
+
+
+class PixelSource(ctypes.Structure):
+    _fields_ = [("projs", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("valid", ctypes.c_void_p), ("n_valid", ctypes.c_void_p),
+                ("order", ctypes.c_void_p), ("n_proj", u32), ("H", u32), ("W", u32), ("n_order", u32)]
 
 
 class MlpGrads(ctypes.Structure):
@@ -54,7 +66,7 @@ class Sampler(ctypes.Structure):
 
 
 NAFB_MAX_RANKS = 8
-STATE_STEP, STATE_SEED_LO, STATE_SEED_HI, STATE_LR, STATE_TICKET, STATE_WORDS = 0, 1, 2, 3, 4, 8
+STATE_STEP, STATE_SEED_LO, STATE_SEED_HI, STATE_TICKET, STATE_TICKET_FWD, STATE_LR, STATE_WORDS = 0, 1, 2, 4, 5, 6, 8   # LR: a double in words 6..7
 XFLAG_ARRIVE, XFLAG_DONE, XFLAG_ERROR, XFLAG_TICKET, XFLAG_TICKET2, XFLAG_WORDS = 0, 8, 16, 17, 18, 32
 
 
@@ -71,7 +83,7 @@ _SIGNATURES = {
     "nafb_peer_close": (ctypes.c_int, [ctypes.c_void_p]),
     "nafb_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
     "nafb_exchange_slice": (ctypes.c_int, [u64, u32, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
-    "nafb_adam_exchange_step": (ctypes.c_int, [ctypes.POINTER(Exchange), ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, u32,
+    "nafb_adam_exchange_step": (ctypes.c_int, [ctypes.POINTER(Exchange), ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, u32,
                                                ctypes.c_float, ctypes.c_void_p]),
     "nafb_abi_version": (ctypes.c_int, []),
     "nafb_last_error": (ctypes.c_char_p, []),
@@ -92,15 +104,38 @@ _SIGNATURES = {
     "nafb_ray_integral_forward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_ray_integral_backward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_mse_loss": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, u32, u32, ctypes.c_float, c_f32p, c_f32p, ctypes.c_int, ctypes.c_void_p]),
-    "nafb_set_mlp_mode": (ctypes.c_int, [ctypes.c_int]),
+    "nafb_ptycho_mask": (ctypes.c_int, [c_f32p, u32, u32, u32, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "nafb_draw_pixels": (ctypes.c_int, [ctypes.POINTER(PixelSource), u32, ctypes.c_void_p, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nafb_density_forward_loss": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), c_f32p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.POINTER(LossTail), ctypes.c_void_p]),
+    "nafb_adam_step_dev": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_float,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "nafb_adam_step": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, u32, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
+}
+
+_DIAG_SIGNATURES = {
     "nafb_microbench": (ctypes.c_int, [ctypes.c_int, c_f32p, u32, ctypes.c_int, c_f32p, ctypes.POINTER(u64), ctypes.c_void_p]),
     "nafb_selftest_umma": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_void_p]),
-    "nafb_adam_step_dev": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
-    "nafb_adam_step": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, u32, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
+    "nafb_diag_last_error": (ctypes.c_char_p, []),
 }
 
 _lib = None
+_diag = None
+
+
+def diag_lib():
+    """libnafb200_diag.so: the tcgen05 known-answer kernel and the L2 micro-benchmarks (kept out of the product library)."""
+    global _diag
+    if _diag is None:
+        if not os.path.exists(DIAG_LIB_PATH):
+            raise RuntimeError(f"{DIAG_LIB_PATH} is missing: run `python -m neuralvolumetricreconstructionformedicalimages_b200.build`")
+        L = ctypes.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in _DIAG_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = L
+    return _diag
 
 
 def exported_symbols():
@@ -217,13 +252,19 @@ def exchange_slice(n: int, rank: int, world: int):
     return int(i0.value), int(i1.value)
 
 
+def lr_words(lr: float):
+    """The two int32 words (low, high) of the double `lr` as the device step state stores it (NAFB_STATE_LR)."""
+    w = np.array([float(lr)], dtype=np.float64).view(np.int32)
+    return int(w[0]), int(w[1])
+
+
 def make_grid(table: torch.Tensor, offsets_np: np.ndarray, D: int, C: int, H: int) -> Grid:
     """offsets_np must stay alive while the returned struct is used (it holds a host pointer)."""
     assert offsets_np.dtype == np.int32 and offsets_np.flags["C_CONTIGUOUS"]
     return Grid(table.data_ptr(), offsets_np.ctypes.data, D, C, offsets_np.shape[0] - 1, H)
 
 
-def make_mlp(weights, biases, in_dim, hidden, out_dim, skips, head: str) -> Mlp:
+def make_mlp(weights, biases, in_dim, hidden, out_dim, skips, head: str, arith: int = ARITH_TC) -> Mlp:
     n = len(weights)
     if n > NAFB_MAX_LAYERS:
         raise RuntimeError(f"num_layers={n} exceeds NAFB_MAX_LAYERS={NAFB_MAX_LAYERS}")
@@ -231,6 +272,7 @@ def make_mlp(weights, biases, in_dim, hidden, out_dim, skips, head: str) -> Mlp:
     m.n_layers, m.in_dim, m.hidden, m.out_dim = n, in_dim, hidden, out_dim
     m.skip_mask = sum(1 << int(s) for s in set(skips) if 0 <= int(s) < 32)
     m.head = ACT[head]
+    m.arith = int(arith)
     for i, (w, b) in enumerate(zip(weights, biases)):
         m.W[i] = w.data_ptr()
         m.b[i] = b.data_ptr()

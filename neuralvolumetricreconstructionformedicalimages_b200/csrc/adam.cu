@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_adam(float *__restrict__ param, float *
 }
 
 __global__ void __launch_bounds__(256) k_adam_dev(float *__restrict__ param, float *__restrict__ grad, float *__restrict__ m_, float *__restrict__ v_,
-                                                  uint64_t n, float beta1, float beta2, float eps, float gscale, int zero_grad, uint32_t *state) {
+                                                  uint64_t n, double beta1, double beta2, double eps, float gscale, int zero_grad, uint32_t *state) {
     __shared__ AdamConst sc;
     if (threadIdx.x == 0) sc = adam_const_from_state(state, beta1, beta2, eps, gscale);
     __syncthreads();
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_adam_dev(float *__restrict__ param, flo
 
 }  // namespace
 
-extern "C" int nafb_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float beta1, float beta2, float eps,
+extern "C" int nafb_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, double beta1, double beta2, double eps,
                                   float grad_scale, int zero_grad, uint32_t *state, nafb_stream_t stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq || !state) NAFB_FAIL(NAFB_ERR_INVALID, "adam_step_dev: null pointer");
     if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0)
@@ -106,14 +106,14 @@ extern "C" int nafb_adam_step_dev(float *param, float *grad, float *exp_avg, flo
     return NAFB_OK;
 }
 
-extern "C" int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float lr, float beta1, float beta2,
-                              float eps, uint32_t step, float grad_scale, int zero_grad, nafb_stream_t stream) {
+extern "C" int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, double lr, double beta1, double beta2,
+                              double eps, uint32_t step, float grad_scale, int zero_grad, nafb_stream_t stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq) NAFB_FAIL(NAFB_ERR_INVALID, "adam_step: null pointer");
     if (step == 0) NAFB_FAIL(NAFB_ERR_INVALID, "adam_step: step is 1-based");
     if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0)
         NAFB_FAIL(NAFB_ERR_INVALID, "adam_step: buffers must be 16-byte aligned");
     if (n == 0) return NAFB_OK;
-    const AdamConst c = make_adam_const((double)lr, beta1, beta2, eps, step, grad_scale);
+    const AdamConst c = make_adam_const(lr, beta1, beta2, eps, step, grad_scale);
     const uint64_t n4 = n >> 2;
     uint64_t blocks = (n4 + 255) / 256;
     const uint64_t cap = (uint64_t)nafb_sm_count() * 8;

@@ -21,15 +21,15 @@ struct AdamConst {
 };
 
 // python-float (double) scalar maths of torch/optim/adam.py, then one cast to fp32; host and device
-__host__ __device__ inline AdamConst make_adam_const(double lr, float beta1, float beta2, float eps, uint32_t step, float gscale) {
-    const double b1 = (double)beta1, b2 = (double)beta2;
+// (beta1 / beta2 / eps / lr arrive as DOUBLES: python's 0.9 is not the double of 0.9f, and 1 - 0.999 would be off by 5e-5)
+__host__ __device__ inline AdamConst make_adam_const(double lr, double b1, double b2, double eps, uint32_t step, float gscale) {
     const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
     AdamConst c;
     c.w1 = (float)(1.0 - b1);
-    c.beta2 = beta2;
+    c.beta2 = (float)b2;
     c.w2 = (float)(1.0 - b2);
-    c.bc2_sqrt = (float)sqrt(bc2);
-    c.eps = eps;
+    c.bc2_sqrt = (float)pow(bc2, 0.5);   // adam.py: bias_correction2 ** 0.5
+    c.eps = (float)eps;
     c.neg_step = (float)(-(lr / bc1));
     c.gscale = gscale;
     return c;
@@ -46,7 +46,8 @@ __device__ __forceinline__ void adam_one(float &p, const float g, float &m, floa
 }
 
 // constants of the step that FOLLOWS the device state (state[STEP] completed steps, learning rate in state[LR])
-__device__ __forceinline__ AdamConst adam_const_from_state(const uint32_t *state, float beta1, float beta2, float eps, float gscale) {
-    return make_adam_const((double)__uint_as_float(state[NAFB_STATE_LR]), beta1, beta2, eps, state[NAFB_STATE_STEP] + 1u, gscale);
+__device__ __forceinline__ AdamConst adam_const_from_state(const uint32_t *state, double beta1, double beta2, double eps, float gscale) {
+    const double lr = __hiloint2double((int)state[NAFB_STATE_LR + 1], (int)state[NAFB_STATE_LR]);
+    return make_adam_const(lr, beta1, beta2, eps, state[NAFB_STATE_STEP] + 1u, gscale);
 }
 #endif

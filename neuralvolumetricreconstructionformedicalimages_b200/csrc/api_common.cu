@@ -24,15 +24,28 @@ int nafb_debug_flags() {
     return cached;
 }
 
+// Per-DEVICE caches (one process may drive several GPUs: the SM count sizes persistent grids, and function attributes such as
+// the dynamic shared-memory limit are per device).
+int nafb_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+    return dev < NAFB_MAX_DEVICES ? dev : NAFB_MAX_DEVICES - 1;
+}
+
 int nafb_sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-        cached = n;
+    static int cached[NAFB_MAX_DEVICES] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev < 0 || dev >= NAFB_MAX_DEVICES) {
+        int n = 0;
+        return cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0 ? n : 148;
     }
-    return cached;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
 }
 
 // Restates the index-mode decision of get_grid_index (hashencoder.cu:55-74) per level:

@@ -18,7 +18,21 @@ void nafb_set_error(const char *fmt, ...);
         if (e_ != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
+// per-device helpers (api_common.cu): SM count of the CURRENT device; index of the current device clamped to the cache size
+constexpr int NAFB_MAX_DEVICES = 64;
 int nafb_sm_count();
+int nafb_current_device();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): `done` is a function-local
+// static bool[NAFB_MAX_DEVICES] of the launcher
+#define NAFB_CONFIGURE_SMEM(done, kernel, bytes, name)                                                         \
+    do {                                                                                                       \
+        const int dev_ = nafb_current_device();                                                                \
+        if (!(done)[dev_]) {                                                                                   \
+            cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+            if (e_ != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e_));          \
+            (done)[dev_] = true;                                                                               \
+        }                                                                                                      \
+    } while (0)
 
 // ----------------------------------------------------------------------------- level table
 // Per-level constants of the multi-resolution grid, evaluated once on the host and passed

@@ -26,13 +26,12 @@ bool nafb_tc_config_ok(const nafb_grid *grid, const nafb_mlp *mlp);
 int nafb_tc_bwd_grid(uint64_t n_tiles);
 uint64_t nafb_tc_stash_bytes(uint64_t n_points);
 int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
-                       float *pts, int32_t *flags, void *stash, cudaStream_t s);
+                       float *pts, int32_t *flags, void *stash, const nafb_loss_tail *tail, cudaStream_t s);
+// the two tensor-core backward kernels: density_bwd_tc.cu (warp-specialised: default) and density_tc.cu (single-role: NAFB_BWD=legacy)
 int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
                        float *grad_table, float *partials, const void *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s);
-int nafb_tc_bwd_grid(uint64_t n_tiles);
-int nafb_launch_fwd_ws(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
-                       float *pts, int32_t *flags, void *stash, cudaStream_t s);
-static int g_mlp_mode = 0;  // 0: tensor cores when the configuration allows, 1: fp32 SIMT everywhere
+int nafb_launch_bwd_ws(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
+                       float *grad_table, float *partials, const void *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s);
 
 namespace {
 
@@ -526,6 +525,7 @@ int check_mlp(const nafb_grid *grid, const nafb_mlp *mlp) {
     if (mlp->skip_mask & (1u | (1u << (mlp->n_layers - 1)) | ~((1u << mlp->n_layers) - 1u)))
         NAFB_FAIL(NAFB_ERR_INVALID, "skips must lie in [1, num_layers-2] (network.py:17-19)");
     if (mlp->head > NAFB_ACT_NONE) NAFB_FAIL(NAFB_ERR_INVALID, "unknown head activation %u", mlp->head);
+    if (mlp->arith > NAFB_ARITH_SIMT) NAFB_FAIL(NAFB_ERR_INVALID, "unknown arithmetic mode %u (nafb_mlp.arith)", mlp->arith);
     for (uint32_t l = 0; l < mlp->n_layers; ++l)
         if (!mlp->W[l] || !mlp->b[l]) NAFB_FAIL(NAFB_ERR_INVALID, "nafb_mlp: layer %u has a null pointer", l);
     return NAFB_OK;
@@ -554,12 +554,8 @@ int launch_fwd(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp
                float *pts, int32_t *flags, cudaStream_t s) {
     const MlpLayout lo = make_layout(mp);
     const size_t smem = fwd_smem_bytes(lo);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_density_fwd<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_forward: %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    static bool configured[NAFB_MAX_DEVICES] = {};
+    NAFB_CONFIGURE_SMEM(configured, (k_density_fwd<SRC, C>), 200 * 1024, "density_forward");
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     if (per_sm > 8) per_sm = 8;
@@ -576,12 +572,8 @@ int launch_bwd(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp
     const MlpLayout lo = make_layout(mp);
     const size_t smem = bwd_smem_bytes(lo);
     if (smem > 227 * 1024) NAFB_FAIL(NAFB_ERR_UNSUPPORTED, "density_backward: %u layers need %zu B of shared memory", mp.n_layers, smem);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_density_bwd<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward: %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    static bool configured[NAFB_MAX_DEVICES] = {};
+    NAFB_CONFIGURE_SMEM(configured, (k_density_bwd<SRC, C>), 227 * 1024, "density_backward");
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
     const int grid = bwd_grid(lo, n_tiles);
     k_density_bwd<SRC, C><<<grid, TILE, smem, s>>>(gp, mp, sp, P, dsig, grad_table, partials);
@@ -605,13 +597,15 @@ int launch_bwd(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp
 
 extern "C" {
 
+static inline bool use_tc(const nafb_grid *grid, const nafb_mlp *mlp) { return mlp->arith == NAFB_ARITH_TC && nafb_tc_config_ok(grid, mlp); }
+
 uint64_t nafb_density_stash_bytes(const nafb_grid *grid, const nafb_mlp *mlp, uint64_t n_points) {
-    if (!grid || !mlp || g_mlp_mode == 1 || !nafb_tc_config_ok(grid, mlp)) return 0;
+    if (!grid || !mlp || !use_tc(grid, mlp)) return 0;
     return nafb_tc_stash_bytes(n_points);
 }
 
-int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src, float *sigma, float *acc,
-                         float *z_vals, float *pts_out, int32_t *flags, void *stash, nafb_stream_t stream) {
+static int density_forward_impl(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src, float *sigma, float *acc,
+                                float *z_vals, float *pts_out, int32_t *flags, void *stash, const nafb_loss_tail *tail, nafb_stream_t stream) {
     GridParams gp;
     int rc = nafb_make_grid_params(grid, &gp);
     if (rc) return rc;
@@ -619,21 +613,30 @@ int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_
     SamplerParams sp;
     uint64_t P = 0;
     if ((rc = nafb_make_sampler_params(smp, src, &sp, &P))) return rc;
+    if (tail) {
+        if (!use_tc(grid, mlp)) NAFB_FAIL(NAFB_ERR_UNSUPPORTED, "density_forward_loss: tensor-core configurations only (launch nafb_density_forward + nafb_mse_loss)");
+        if (!acc || !tail->target || !tail->loss_out || !tail->ticket) NAFB_FAIL(NAFB_ERR_INVALID, "density_forward_loss: null pointer");
+        if (P == 0) NAFB_FAIL(NAFB_ERR_INVALID, "density_forward_loss: empty batch");
+    }
     if (P == 0) return NAFB_OK;
     if (src != NAFB_SRC_RAYS && (acc || z_vals || pts_out)) NAFB_FAIL(NAFB_ERR_INVALID, "density_forward: acc/z_vals/pts_out need the RAYS source");
     cudaStream_t s = (cudaStream_t)stream;
     if (src == NAFB_SRC_VOXELS) stash = nullptr;            // forward-only source (its tiles are lattice blocks, not point ranges)
-    if (g_mlp_mode != 1 && nafb_tc_config_ok(grid, mlp))   // mode 2: warp-specialised forward (producer / MMA / epilogue warps)
-        return (g_mlp_mode == 2 ? nafb_launch_fwd_ws : nafb_launch_fwd_tc)(gp, *mlp, sp, src, P, sigma, acc, z_vals, pts_out, flags, stash, s);
+    if (use_tc(grid, mlp)) return nafb_launch_fwd_tc(gp, *mlp, sp, src, P, sigma, acc, z_vals, pts_out, flags, stash, tail, s);
 #define CALL(S_, C_) launch_fwd<S_, C_>(gp, *mlp, sp, P, sigma, acc, z_vals, pts_out, flags, s)
     DISPATCH_SRC_C(src, gp.C, CALL);
 #undef CALL
 }
 
-int nafb_set_mlp_mode(int mode) {
-    if (mode < 0 || mode > 2) NAFB_FAIL(NAFB_ERR_INVALID, "set_mlp_mode: mode must be 0 (tensor cores), 1 (fp32 SIMT) or 2 (tensor cores, warp-specialised forward)");
-    g_mlp_mode = mode;
-    return NAFB_OK;
+int nafb_density_forward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, int src, float *sigma, float *acc,
+                         float *z_vals, float *pts_out, int32_t *flags, void *stash, nafb_stream_t stream) {
+    return density_forward_impl(grid, mlp, smp, src, sigma, acc, z_vals, pts_out, flags, stash, nullptr, stream);
+}
+
+int nafb_density_forward_loss(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, float *acc, int32_t *flags, void *stash,
+                              const nafb_loss_tail *loss, nafb_stream_t stream) {
+    if (!loss) NAFB_FAIL(NAFB_ERR_INVALID, "density_forward_loss: null loss descriptor");
+    return density_forward_impl(grid, mlp, smp, NAFB_SRC_RAYS, nullptr, acc, nullptr, nullptr, flags, stash, loss, stream);
 }
 
 uint64_t nafb_density_backward_workspace_bytes(const nafb_mlp *mlp) {
@@ -655,21 +658,15 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
     if (P == 0) return NAFB_OK;
     if (!dsigma_or_dacc || !grads || !workspace) NAFB_FAIL(NAFB_ERR_INVALID, "density_backward: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
-    if (g_mlp_mode == 0 && nafb_tc_config_ok(grid, mlp)) {
+    if (use_tc(grid, mlp)) {
         const int grid_tc = nafb_tc_bwd_grid((P + TILE - 1) / TILE);
         const MlpLayout lo = make_layout(*mlp);
         long long *stamps = reinterpret_cast<long long *>((char *)workspace + partials_bytes(lo));
-        // (the tensor-core kernel reduces the per-CTA MLP gradients itself, behind a grid-wide barrier: no second launch)
-        static int separate = -1;   // debug knob: NAFB_BWD_REDUCE=kernel -> the reduction as a separate launch
-        if (separate < 0) { const char *e = getenv("NAFB_BWD_REDUCE"); separate = e && e[0] == 'k'; }
-        if (separate) {
-            nafb_mlp_grads none = {};
-            if ((rc = nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps, grid_tc, none, s))) return rc;
-            k_reduce_partials<<<(lo.total + 31) / 32, 32 * RP_SLICES, 0, s>>>(*mlp, *grads, (const float *)workspace, grid_tc);
-            NAFB_CHECK_LAUNCH("density_backward(reduce)");
-            return NAFB_OK;
-        }
-        return nafb_launch_bwd_tc(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps, grid_tc, *grads, s);
+        // (the tensor-core kernels reduce the per-CTA MLP gradients themselves, behind a grid-wide barrier: no second launch)
+        static int legacy = -1;   // experiment knob (process-wide, read once): NAFB_BWD=legacy -> the single-role kernel of density_tc.cu
+        if (legacy < 0) { const char *e = getenv("NAFB_BWD"); legacy = e && e[0] == 'l'; }
+        return (legacy ? nafb_launch_bwd_tc : nafb_launch_bwd_ws)(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps,
+                                                                  grid_tc, *grads, s);
     }
 #define CALL(S_, C_) launch_bwd<S_, C_>(gp, *mlp, sp, P, dsigma_or_dacc, grad_table, *grads, (float *)workspace, s)
     switch (gp.C) {

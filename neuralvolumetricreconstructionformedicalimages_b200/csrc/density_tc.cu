@@ -18,357 +18,12 @@
 // are read out once.  Products are bf16x3 (hi*hi + hi*lo + lo*hi): |rel err| ~ 2^-16 per product.
 // Bias, LeakyReLU, the 1-wide head, its gradient and the bias / head-weight gradients are fp32
 // SIMT work in the epilogues (TMEM -> registers -> shared memory operand of the next MMA).
-#include "common.cuh"
-#include "sampler.cuh"
-#include "umma.cuh"
+#include "density_tc.cuh"
+#include "loss.cuh"
 
-// profiling knobs (env NAFB_DEBUG_SKIP, read once): bit 0 = skip the gradient scatter, bit 1 = skip the table
-// gather (synthetic encodings), bit 4 = no warp aggregation, bit 5 = phase time stamps of the backward kernel,
-// bits 8-13 / 16-21 = aggregation thresholds.  Results are wrong with bits 0/1 set; used only to attribute kernel time.
-int nafb_debug_flags();
+using namespace tc;
 
 namespace {
-
-constexpr int TILE = 128;
-constexpr int NT = 256;
-#ifndef FWD_CTAS
-#define FWD_CTAS 3   // forward CTAs per SM (measured at chest_50: 2 -> 93 us, 3 -> 83 us, 4 -> 125 us: the L1 left over by 4 x 50 KB of shared memory is too small for the coarse levels)
-#endif
-constexpr int NT_B = 288;  // backward: 8 epilogue warps + 1 MMA-issue warp
-constexpr uint32_t LBO = 128;  // bytes between adjacent 8-column chunks of a row group
-
-// ---- weights in shared memory (bf16 hi / lo, rows = output feature, chunks along the input)
-constexpr uint32_t W0_OFF = 0, W0_SBO = 512;      // 32 x 32
-constexpr uint32_t W1_OFF = 2048, W1_SBO = 512;   // 32 x 32
-constexpr uint32_t W2_OFF = 4096, W2_SBO = 1024;  // 32 x 64
-constexpr uint32_t W_HALF = 8192;                 // bytes per (hi | lo) weight image
-
-struct SmallParams {   // fp32: biases of the hidden layers, head weights + bias
-    float b0[32], b1[32], b2[32], w3[32], b3;
-};
-
-__device__ __forceinline__ void load_weight_images(const nafb_mlp &mp, uint8_t *w_hi, uint8_t *w_lo, SmallParams *sp) {
-    // one 16-byte chunk (8 consecutive inputs of one output row) per iteration
-    auto fill = [&](const float *__restrict__ W, int in_dim, uint32_t off, uint32_t sbo) {
-        const int chunks = in_dim / 8;
-        for (int i = threadIdx.x; i < 32 * chunks; i += blockDim.x) {
-            const int row = i / chunks, c = i - row * chunks;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldg(W + row * in_dim + c * 8 + k);
-            umma::store_chunk_split(w_hi, w_lo, off + umma::canon_off(row, c, LBO, sbo), v);
-        }
-    };
-    fill(mp.W[0], 32, W0_OFF, W0_SBO);
-    fill(mp.W[1], 32, W1_OFF, W1_SBO);
-    fill(mp.W[2], 64, W2_OFF, W2_SBO);
-    if (threadIdx.x < 32) {
-        sp->b0[threadIdx.x] = __ldg(mp.b[0] + threadIdx.x);
-        sp->b1[threadIdx.x] = __ldg(mp.b[1] + threadIdx.x);
-        sp->b2[threadIdx.x] = __ldg(mp.b[2] + threadIdx.x);
-        sp->w3[threadIdx.x] = __ldg(mp.W[3] + threadIdx.x);
-        if (threadIdx.x == 0) sp->b3 = __ldg(mp.b[3]);
-    }
-}
-
-// gather the 16 encoding features [16*half, 16*half+16) of one point into two chunks.
-// The gather is latency-bound (an L2 round trip per level when the loads of one level are all a thread has in flight: ncu
-// shows 0.27 L1TEX wavefronts/clk/SM and 36 % L2 throughput with 44 % of the warp samples waiting on these loads), so the
-// loop is software-pipelined: the loads of level li + GATHER_DEPTH are issued before level li is consumed.
-#ifndef GATHER_DEPTH
-#define GATHER_DEPTH 1
-#endif
-template <int C>
-__device__ __forceinline__ void gather_half(const GridParams &gp, const float (&x01)[3], int half, float (&enc)[16]) {
-    constexpr int LH = 16 / C;  // levels per half
-    float v[LH][8][C];          // fully unrolled: only GATHER_DEPTH + 1 levels are live at any time
-    auto issue = [&](const int li) {
-        const LevelParams lp = gp.lv[half * LH + li];
-        const float *__restrict__ tab = gp.table + (size_t)lp.offset * C;
-        uint32_t g[3];
-        float f[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
-        const uint32_t par = addr_parity8(tab);
-        const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
-        uint32_t e[8];
-        cell_entries8(lp, ct, e);
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j)   // (y, z) corner; the two x-neighbours share one access when adjacent + aligned
-            load_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[li][2 * j], v[li][2 * j + 1]);
-    };
-    auto consume = [&](const int li) {
-        const float scale = gp.lv[half * LH + li].scale;
-        uint32_t g;
-        float f[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) locate(x01[d], scale, g, f[d]);
-        float res[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) res[c] = 0.f;
-#pragma unroll
-        for (uint32_t idx = 0; idx < 8; ++idx) {
-            float w = 1.0f;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
-#pragma unroll
-            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[li][idx][c], res[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) enc[li * C + c] = res[c];
-    };
-#pragma unroll
-    for (int li = 0; li < GATHER_DEPTH && li < LH; ++li) issue(li);
-#pragma unroll
-    for (int li = 0; li < LH; ++li) {
-        if (li + GATHER_DEPTH < LH) issue(li + GATHER_DEPTH);
-        consume(li);
-    }
-}
-
-// Gradient scatter of ONE level of one point: d(encoding) of the level is read from the point's TMEM lane
-// (`taddr`: C columns), the 8 corner reductions go to the gradient table.  One copy of this code serves all
-// levels and all call sites (__noinline__): the backward kernel calls it from the wait slots of the NEXT tile's
-// MMA chain, so the reductions drain through the LSU while the tensor core and the epilogues work.
-//
-// Coarse levels are WARP-AGGREGATED: the 32 lanes of a warp hold 32 consecutive sample points (for the
-// ray source: consecutive samples of one ray), which fall into a few grid cells only.  Lanes of one
-// cell form a contiguous run; a segmented suffix sum over the run (5 shuffle steps per value) leaves
-// the run totals of the 8 corners x C channels in the run's first lane, which issues the only
-// reductions of the run.  The L2 atomic unit serialises per address (and the few hot lines of a coarse
-// level live in a handful of L2 slices), so the number of reductions -- not their bytes -- is what the
-// backward pass pays for.  The choice is made per warp and level from the number of runs (ballot).
-constexpr int AGG_LEVELS = 8;      // levels 0 .. AGG_LEVELS-1 may be aggregated
-constexpr int AGG_MAX_RUNS = 20;   // aggregate when the warp has at most this many runs
-// (both can be overridden for experiments through NAFB_DEBUG_SKIP: bits 8-13 = levels + 1, bits 16-21 = runs + 1)
-
-template <int C>
-__device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, const int l, const float x0, const float x1, const float x2,
-                                         const uint32_t taddr, const bool valid, const int agg_max_runs, float *__restrict__ grad_table) {
-    const unsigned lane = threadIdx.x & 31u;
-    float ge[C];
-    umma::tmem_ldn<C>(taddr, ge);
-    const LevelParams lp = lvs[l];
-    float *tab = grad_table + (size_t)lp.offset * C;
-    const uint32_t par = addr_parity8(tab);
-    uint32_t g[3];
-    float f[3];
-    locate(x0, lp.scale, g[0], f[0]);
-    locate(x1, lp.scale, g[1], f[1]);
-    locate(x2, lp.scale, g[2], f[2]);
-    const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
-    uint32_t e[8];
-    cell_entries8(lp, ct, e);
-    umma::tmem_wait_ld();
-    if (agg_max_runs > 0) {
-        // runs of equal cells among consecutive lanes (invalid lanes: a run of their own, never issued)
-        const uint32_t k0 = valid ? (g[0] | (g[1] << 16)) : 0xffffffffu, k1 = valid ? g[2] : 0xffffffffu;
-        const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
-        const bool head = lane == 0 || p0 != k0 || p1 != k1;
-        const uint32_t heads = __ballot_sync(0xffffffffu, head);
-        if (__popc(heads) <= agg_max_runs) {
-            float v[8][C];
-#pragma unroll
-            for (uint32_t idx = 0; idx < 8; ++idx) {
-                float w = 1.0f;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
-#pragma unroll
-                for (int c = 0; c < C; ++c) v[idx][c] = valid ? __fmul_rn(w, ge[c]) : 0.f;
-            }
-            const uint32_t above = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));  // bit j: lane+1+j starts a new run
-            // only as many doubling steps as the longest run of the warp needs
-            const uint32_t my_len = head ? (above ? (uint32_t)__ffs(above) : 32u - lane) : 0u;
-            const uint32_t max_len = __reduce_max_sync(0xffffffffu, my_len);
-            for (uint32_t o = 1; o < max_len; o <<= 1) {
-                const bool same = (lane + o < 32) && ((above & ((1u << o) - 1u)) == 0u);
-#pragma unroll
-                for (uint32_t idx = 0; idx < 8; ++idx)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float up = __shfl_down_sync(0xffffffffu, v[idx][c], o);
-                        if (same) v[idx][c] += up;
-                    }
-            }
-            if (head && valid) {
-#pragma unroll
-                for (uint32_t j = 0; j < 4; ++j)
-                    red_add_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[2 * j], v[2 * j + 1]);
-            }
-            return;
-        }
-    }
-    if (valid) {
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            float v0[C], v1[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                // same products as the corner loop of the reference: ((1 * a0) * a1) * a2 evaluated as (a0 * a1) * a2
-                v0[c] = __fmul_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.0f, f[0]), (j & 1u) ? f[1] : __fsub_rn(1.0f, f[1])), (j >> 1) ? f[2] : __fsub_rn(1.0f, f[2])), ge[c]);
-                v1[c] = __fmul_rn(__fmul_rn(__fmul_rn(f[0], (j & 1u) ? f[1] : __fsub_rn(1.0f, f[1])), (j >> 1) ? f[2] : __fsub_rn(1.0f, f[2])), ge[c]);
-            }
-            red_add_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v0, v1);
-        }
-    }
-}
-
-// Backward pass without a stash: gather the thread's 16 encoding columns level by level (rolled loop, one copy of
-// the code) and drop them as bf16 (hi, lo) into the operand tile.
-template <int C>
-__device__ __noinline__ void gather_half_to_smem(const LevelParams *__restrict__ lvs, const float *__restrict__ table, const float x0,
-                                                 const float x1, const float x2, const int half, uint8_t *hi, uint8_t *lo, const uint32_t row,
-                                                 const uint32_t chunk0, const uint32_t sbo) {
-    constexpr int LH = 16 / C;
-#pragma unroll 1
-    for (int li = 0; li < LH; ++li) {
-        const LevelParams lp = lvs[half * LH + li];
-        const float *__restrict__ tab = table + (size_t)lp.offset * C;
-        uint32_t g[3];
-        float f[3];
-        locate(x0, lp.scale, g[0], f[0]);
-        locate(x1, lp.scale, g[1], f[1]);
-        locate(x2, lp.scale, g[2], f[2]);
-        const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
-        uint32_t e[8];
-        cell_entries8(lp, ct, e);
-        float v[8][C];
-#pragma unroll
-        for (uint32_t idx = 0; idx < 8; ++idx) load_entry<C>(tab, e[idx], v[idx]);
-        float res[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) res[c] = 0.f;
-#pragma unroll
-        for (uint32_t idx = 0; idx < 8; ++idx) {
-            float w = 1.0f;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
-#pragma unroll
-            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[idx][c], res[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const uint32_t col = (uint32_t)(li * C + c);
-            const uint32_t off = umma::canon_off(row, chunk0 + 2 * half + (col >> 3), LBO, sbo) + (col & 7u) * 2u;
-            __nv_bfloat16 h, lw;
-            umma::split_bf16(res[c], h, lw);
-            *reinterpret_cast<__nv_bfloat16 *>(hi + off) = h;
-            *reinterpret_cast<__nv_bfloat16 *>(lo + off) = lw;
-        }
-    }
-}
-
-// write this thread's 16 values (two chunks) of a 32-wide block starting at chunk `chunk0`
-__device__ __forceinline__ void store_half_row(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo, const float (&v)[16]) {
-    umma::store_chunk_split(hi, lo, umma::canon_off(row, chunk0 + 2 * half, LBO, sbo), v);
-    umma::store_chunk_split(hi, lo, umma::canon_off(row, chunk0 + 2 * half + 1, LBO, sbo), v + 8);
-}
-
-// ---- encoding stash: what a training forward leaves for the backward pass (16 KB per 128-point tile):
-// the bf16 (hi | lo) images of the tile's encodings in the canonical layout with 4 chunks per row
-// (SBO 512), i.e. byte-for-byte what the tensor core consumed.  A warp writes / reads whole 128-byte
-// lines; the backward pass then needs no table gather at all.
-constexpr uint32_t ST_SBO = 512, ST_HALF = 8192, ST_TILE = 16384;
-
-__device__ __forceinline__ void store_half_row_and_stash(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo,
-                                                         const float (&v)[16], uint8_t *stash_tile) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint4 h, l;
-        umma::split_chunk(v + 8 * c, h, l);
-        const uint32_t off = umma::canon_off(row, chunk0 + 2 * half + c, LBO, sbo);
-        *reinterpret_cast<uint4 *>(hi + off) = h;
-        *reinterpret_cast<uint4 *>(lo + off) = l;
-        if (stash_tile) {
-            const uint32_t so = umma::canon_off(row, 2 * half + c, LBO, ST_SBO);
-            *reinterpret_cast<uint4 *>(stash_tile + so) = h;   // default policy: the backward pass finds it in L2
-            *reinterpret_cast<uint4 *>(stash_tile + ST_HALF + so) = l;
-        }
-    }
-}
-
-__device__ __forceinline__ void load_stash_half_row(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo,
-                                                    const uint8_t *stash_tile) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const uint32_t so = umma::canon_off(row, 2 * half + c, LBO, ST_SBO);
-        const uint4 h = __ldcs(reinterpret_cast<const uint4 *>(stash_tile + so));
-        const uint4 l = __ldcs(reinterpret_cast<const uint4 *>(stash_tile + ST_HALF + so));
-        const uint32_t off = umma::canon_off(row, chunk0 + 2 * half + c, LBO, sbo);
-        *reinterpret_cast<uint4 *>(hi + off) = h;
-        *reinterpret_cast<uint4 *>(lo + off) = l;
-    }
-}
-
-// sign of the stored activations (hi part is enough): slope of LeakyReLU at h
-__device__ __forceinline__ void lrelu_slopes(const uint8_t *hi, uint32_t row, uint32_t chunk0, int half, uint32_t sbo, float (&s)[16]) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(hi + umma::canon_off(row, chunk0 + 2 * half + c, LBO, sbo));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            // bf16 > 0  <=>  sign bit clear and not zero
-            const uint32_t a = w[i] & 0xFFFFu, b = w[i] >> 16;
-            s[c * 8 + 2 * i] = (a != 0u && !(a & 0x8000u)) ? 1.0f : 0.01f;
-            s[c * 8 + 2 * i + 1] = (b != 0u && !(b & 0x8000u)) ? 1.0f : 0.01f;
-        }
-    }
-}
-
-// column sums over the 32 lanes of a warp of 16 per-lane values: afterwards lane (j & 15) and
-// lane (j & 15) + 16 hold the sum of column j.  Recursive halving: 8+4+2+1+1 = 16 shuffles.
-__device__ __forceinline__ float warp_colsum16(const float (&v)[16], unsigned lane) {
-    float a[8];
-    {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = up ? v[i] : v[i + 8];
-            const float keep = up ? v[i + 8] : v[i];
-            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    float b[4];
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = up ? a[i] : a[i + 4];
-            const float keep = up ? a[i + 4] : a[i];
-            b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    float c[2];
-    {
-        const bool up = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = up ? b[i] : b[i + 2];
-            const float keep = up ? b[i + 2] : b[i];
-            c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    float d;
-    {
-        const bool up = lane & 2;
-        const float send = up ? c[0] : c[1];
-        const float keep = up ? c[1] : c[0];
-        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    return d;  // column index held by this lane: colsum_index(lane)
-}
-// which of the 16 columns ends up in `lane` after warp_colsum16
-__device__ __forceinline__ int colsum_index(unsigned lane) {
-    return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-}
-
-struct TileCtl {
-    uint64_t mbar;
-    uint32_t tmem_base;
-    uint32_t pad;
-};
 
 // ================================================================================ forward
 // smem: X_hi | X_lo : 128 rows x 8 chunks [enc(0-3) | h(4-7)], SBO 1024 -> 16 KB each
@@ -379,7 +34,7 @@ template <int SRC, int C>
 __global__ void __launch_bounds__(NT, FWD_CTAS) k_density_fwd_tc(const GridParams gp, const nafb_mlp mp, const SamplerParams sp, const uint64_t P,
                                                           float *__restrict__ sigma, float *__restrict__ acc_out, float *__restrict__ z_out,
                                                           float *__restrict__ pts_out, int32_t *__restrict__ flags, uint8_t *__restrict__ stash,
-                                                          const int dbg) {
+                                                          const int dbg, const nafb_loss_tail tail) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *X_hi = smem, *X_lo = X_hi + FX_HALF;
     uint8_t *W_hi = X_lo + FX_HALF, *W_lo = W_hi + W_HALF;
@@ -432,6 +87,10 @@ __global__ void __launch_bounds__(NT, FWD_CTAS) k_density_fwd_tc(const GridParam
                 gather_half<C>(gp, x01, half, enc);
             }
             store_half_row_and_stash(X_hi, X_lo, r, 0, half, FX_SBO, enc, stash ? stash + tile * ST_TILE : nullptr);
+            if (stash && half == 1) {   // tail of the stash tile: the normalised position (the backward scatter needs it again)
+                float *tail = reinterpret_cast<float *>(stash + tile * ST_TILE + ST_TAIL_X01);
+                tail[r] = x01[0]; tail[128 + r] = x01[1]; tail[256 + r] = x01[2];
+            }
         }
         // ---------------- layer 0: enc . W0^T
         umma::fence_proxy_async();
@@ -500,14 +159,16 @@ __global__ void __launch_bounds__(NT, FWD_CTAS) k_density_fwd_tc(const GridParam
                 if (!(fabsf(y) <= 3.4028234e38f)) bad |= 2;
             }
             if constexpr (SRC == NAFB_SRC_RAYS) {
-                if (acc_out || z_out) {
+                if (acc_out || z_out || stash) {
                     float contrib = 0.f;
                     uint32_t ray = 0xffffffffu;
                     if (valid) {
                         ray = (uint32_t)(p / sp.n_samples);
                         const uint32_t i = (uint32_t)(p - (uint64_t)ray * sp.n_samples);
                         const RayRegs R = load_ray(sp, ray);
-                        contrib = __fmul_rn(y, ray_delta(sp, R, ray, i));  // render.py:201
+                        const float delta = ray_delta(sp, R, ray, i);
+                        if (stash) reinterpret_cast<float *>(stash + tile * ST_TILE + ST_TAIL_DELTA)[r] = delta;
+                        contrib = __fmul_rn(y, delta);  // render.py:201
                         if (z_out)
                             z_out[p] = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
                                                 jitter_for(sp, ray));
@@ -531,6 +192,23 @@ __global__ void __launch_bounds__(NT, FWD_CTAS) k_density_fwd_tc(const GridParam
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 32);
+    // ---- loss tail (training): the last CTA to retire sees every ray integral (atomics into acc_out, made visible by the
+    // fence + ticket) and evaluates the masked chunk-wise MSE and d loss / d acc -- what a separate nafb_mse_loss launch did.
+    if (tail.ticket) {
+        __shared__ uint32_t s_last;
+        if (t == 0) {
+            __threadfence();
+            s_last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            float *s_mean = reinterpret_cast<float *>(smem), *s_cnt = s_mean + MSE_GROUP;   // the operand tiles are dead by now
+            const uint32_t n = sp.n_rays, chunk = (tail.chunk == 0 || tail.chunk > n) ? n : tail.chunk;
+            mse_loss_block(acc_out, tail.target, tail.mask, n, chunk, tail.gscale, tail.loss_out, tail.dacc, tail.zero_pred, s_mean, s_cnt);
+            if (t == 0) *tail.ticket = 0u;
+        }
+    }
 }
 
 // ================================================================================ backward
@@ -955,17 +633,14 @@ bool tc_config_ok(const nafb_grid *grid, const nafb_mlp *mlp) {
 
 template <int SRC, int C>
 int launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, float *sigma, float *acc, float *z, float *pts,
-                  int32_t *flags, uint8_t *stash, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_density_fwd_tc<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
-        if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_forward(tc): %s", cudaGetErrorString(e));
-        configured = true;
-    }
+                  int32_t *flags, uint8_t *stash, const nafb_loss_tail &tail, cudaStream_t s) {
+    static bool configured[NAFB_MAX_DEVICES] = {};
+    NAFB_CONFIGURE_SMEM(configured, (k_density_fwd_tc<SRC, C>), (int)FWD_SMEM, "density_forward(tc)");
     const uint64_t n_tiles = SRC == NAFB_SRC_VOXELS ? (uint64_t)((sp.i1 - sp.i0 + 3) / 4) * ((sp.n2 + 3) / 4) * ((sp.n3 + 7) / 8) : (P + TILE - 1) / TILE;
     const uint64_t cap = (uint64_t)nafb_sm_count() * FWD_CTAS;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags, stash, nafb_debug_flags());
+    const int dbg = nafb_debug_flags();
+    k_density_fwd_tc<SRC, C><<<grid, NT, FWD_SMEM, s>>>(gp, mp, sp, P, sigma, acc, z, pts, flags, stash, dbg, tail);
     NAFB_CHECK_LAUNCH("density_forward(tc)");
     return NAFB_OK;
 }
@@ -983,8 +658,10 @@ int nafb_tc_bwd_grid(uint64_t n_tiles) {
 uint64_t nafb_tc_stash_bytes(uint64_t n_points) { return (n_points + TILE - 1) / TILE * (uint64_t)ST_TILE; }
 
 int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
-                       float *pts, int32_t *flags, void *stash, cudaStream_t s) {
-#define CALL(S_, C_) launch_fwd_tc<S_, C_>(gp, mp, sp, P, sigma, acc, z, pts, flags, (uint8_t *)stash, s)
+                       float *pts, int32_t *flags, void *stash, const nafb_loss_tail *tail_in, cudaStream_t s) {
+    nafb_loss_tail tail = {};
+    if (tail_in) tail = *tail_in;
+#define CALL(S_, C_) launch_fwd_tc<S_, C_>(gp, mp, sp, P, sigma, acc, z, pts, flags, (uint8_t *)stash, tail, s)
     switch (gp.C) {
         case 1: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 1) : src == NAFB_SRC_RAYS ? CALL(NAFB_SRC_RAYS, 1) : CALL(NAFB_SRC_VOXELS, 1);
         case 2: return src == NAFB_SRC_POINTS ? CALL(NAFB_SRC_POINTS, 2) : src == NAFB_SRC_RAYS ? CALL(NAFB_SRC_RAYS, 2) : CALL(NAFB_SRC_VOXELS, 2);
@@ -997,12 +674,8 @@ int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerPa
 template <int SRC, int C>
 static int launch_bwd_tc_t(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, const float *dsig, float *grad_table,
                            float *partials, const uint8_t *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_density_bwd_tc<SRC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
-        if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    static bool configured[NAFB_MAX_DEVICES] = {};
+    NAFB_CONFIGURE_SMEM(configured, (k_density_bwd_tc<SRC, C>), (int)BWD_SMEM, "density_backward(tc)");
     // behind the partials: 4096 B of phase time stamps (debug), then the two words of the grid barrier
     uint32_t *sync = gr.gW[0] || gr.gb[0] || gr.gW[1] ? reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(stamps) + 4096) : nullptr;
     k_density_bwd_tc<SRC, C><<<grid, NT_B, BWD_SMEM, s>>>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, nafb_debug_flags(), gr, sync);

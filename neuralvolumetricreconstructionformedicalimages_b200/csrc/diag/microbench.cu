@@ -1,7 +1,7 @@
 // microbench.cu -- measured denominators for the L2-resident gather / scatter roofline
 // (first-GPU-call checklist item 6): random vector loads and random
 // no-return float reductions over a resident table, plus contended variants.
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace {
 

@@ -4,8 +4,8 @@
 //   D2[p][k] = sum_{o<32}  A[p][o] * W[o][k], k<64  A K-major,  B MN-major  (input gradient)
 //   D3[m][n] = sum_{p<128} A[p][m] * X[p][n], m<128 A MN-major, B MN-major  (weight gradient)
 // A [128,128], X [128,32], W [32,64] fp32 row-major in global memory.
-#include "common.cuh"
-#include "umma.cuh"
+#include "../common.cuh"
+#include "../umma.cuh"
 
 namespace {
 

@@ -41,7 +41,8 @@ struct ExchangeParams {
     uint64_t n4, s0, s1;   // float4 units
     AdamConst c;           // host-evaluated constants (state == nullptr)
     uint32_t *state;       // device step state, or nullptr
-    float beta1, beta2, eps, gscale;
+    double beta1, beta2, eps;
+    float gscale;
     float *mc_param;       // NVLS multicast addresses of the parameter vector / this parity's gradient, or nullptr
     const float *mc_grad;
     float *stage[MAXR];    // push mode: every rank's staging area [W][slot4 float4] (slot r of rank w: written by rank r)
@@ -359,7 +360,7 @@ int nafb_exchange_slice(uint64_t n, uint32_t rank, uint32_t world, uint64_t *i0,
     return NAFB_OK;
 }
 
-int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale,
+int nafb_adam_exchange_step(const nafb_exchange *x, double lr, double beta1, double beta2, double eps, uint32_t step, float grad_scale,
                             nafb_stream_t stream) {
     if (!x) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: null descriptor");
     if (x->world < 1 || x->world > NAFB_MAX_RANKS || x->rank >= x->world) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: world %u / rank %u", x->world, x->rank);
@@ -380,7 +381,7 @@ int nafb_adam_exchange_step(const nafb_exchange *x, float lr, float beta1, float
     int rc = nafb_exchange_slice(x->n, x->rank, x->world, &i0, &i1);
     if (rc) return rc;
     P.n4 = x->n >> 2; P.s0 = i0 >> 2; P.s1 = i1 >> 2;
-    P.c = make_adam_const((double)lr, beta1, beta2, eps, step ? step : 1u, grad_scale);
+    P.c = make_adam_const(lr, beta1, beta2, eps, step ? step : 1u, grad_scale);
     P.state = x->state; P.beta1 = beta1; P.beta2 = beta2; P.eps = eps; P.gscale = grad_scale;
     if ((x->mc_param != nullptr) != (x->mc_grad != nullptr)) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: mc_param and mc_grad go together");
     if (((uintptr_t)x->mc_param | (uintptr_t)x->mc_grad) & 15) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: multicast addresses must be 16-byte aligned");

@@ -5,6 +5,7 @@
 // render()/raw2outputs()/calc_mse_loss() operators.
 #include "common.cuh"
 #include "sampler.cuh"
+#include "loss.cuh"
 
 namespace {
 
@@ -87,50 +88,13 @@ __global__ void __launch_bounds__(256) k_generate_rays(const SamplerParams sp, f
     o[1] = make_float4(R.d[1], R.d[2], R.near, R.far);
 }
 
-// Single block, deterministic: loss = sum_chunks mean_{valid in chunk} (target - pred)^2   (train.py:69-127, loss.py:26-46).
-// One warp per chunk (all chunks of a group in flight at once); the chunk means are then added in chunk order by one
-// thread, as the reference's python loop does.  `zero_pred`: pred is cleared after it has been consumed (the fused engine
-// accumulates the next step's projections into the same buffer).
-constexpr int MSE_GROUP = 1024;   // chunks per pass
-
+// Single block: see loss.cuh
 __global__ void __launch_bounds__(1024) k_mse_loss(float *__restrict__ pred, const float *__restrict__ target,
                                                    const uint8_t *__restrict__ mask, uint32_t n, uint32_t chunk, float gscale,
                                                    float *__restrict__ loss_out, float *__restrict__ dpred, int zero_pred) {
     __shared__ float s_mean[MSE_GROUP];
     __shared__ float s_cnt[MSE_GROUP];
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const uint32_t n_chunks = (n + chunk - 1) / chunk;
-    float total = 0.f, total_cnt = 0.f;
-    for (uint32_t g0 = 0; g0 < n_chunks; g0 += MSE_GROUP) {
-        const uint32_t g1 = g0 + MSE_GROUP < n_chunks ? g0 + MSE_GROUP : n_chunks;
-        for (uint32_t c = g0 + warp; c < g1; c += n_warps) {
-            const uint32_t c0 = c * chunk, c1 = c0 + chunk < n ? c0 + chunk : n;
-            float s = 0.f, cnt = 0.f;
-            for (uint32_t i = c0 + lane; i < c1; i += 32) {
-                if (!mask || mask[i]) {
-                    const float d = __fsub_rn(target[i], pred[i]);
-                    s = __fmaf_rn(d, d, s);
-                    cnt += 1.f;
-                }
-            }
-            s = warp_sum(s);
-            cnt = warp_sum(cnt);
-            const float inv = 1.0f / cnt;   // an empty chunk gives mean(empty) = NaN in torch; keep that behaviour
-            if (lane == 0) { s_mean[c - g0] = s / cnt; s_cnt[c - g0] = cnt; }
-            for (uint32_t i = c0 + lane; i < c1; i += 32) {
-                if (dpred) {
-                    const bool m = !mask || mask[i];
-                    dpred[i] = m ? gscale * 2.0f * __fsub_rn(pred[i], target[i]) * inv : 0.f;
-                }
-                if (zero_pred) pred[i] = 0.f;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-            for (uint32_t c = 0; c < g1 - g0; ++c) { total += s_mean[c]; total_cnt += s_cnt[c]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { loss_out[0] = total; loss_out[1] = total_cnt; }
+    mse_loss_block(pred, target, mask, n, chunk, gscale, loss_out, dpred, zero_pred, s_mean, s_cnt);
 }
 
 }  // namespace

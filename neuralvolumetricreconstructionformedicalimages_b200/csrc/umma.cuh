@@ -116,6 +116,16 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) 
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// the same with the barrier id as an immediate: ptxas then reserves only the ids that are really used
+template <int ID>
+__device__ __forceinline__ void named_bar_sync_imm(uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(threads) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void named_bar_arrive_imm(uint32_t threads) {
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(threads) : "memory");
+}
+
 // ---- tensor memory
 // one full warp: allocate `ncols` (power of two >= 32) columns, base address written to *slot (smem)
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {

@@ -33,6 +33,7 @@ The voxel query shards by slabs of the outermost index and needs no collective.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -89,6 +90,10 @@ class EventTimer:
         return {k: (t / c, c) for k, (t, c) in acc.items()}
 
 
+class PeerSetupError(RuntimeError):
+    """Peer-memory exchange could not be set up on every rank (raised on ALL ranks together)."""
+
+
 class PeerExchange:
     """Peer-mapped flat buffers of all ranks + the descriptors of nafb_adam_exchange_step (one per gradient parity).
 
@@ -103,34 +108,75 @@ class PeerExchange:
     FLAG_BYTES = 256
 
     def __init__(self, n, device, group, rank, world, backend="ipc"):
+        """Set-up is COLLECTIVE and staged so that a failure on one rank never leaves the others inside a collective that
+        rank skipped: every stage that can fail locally is followed by an all-reduce(MIN) of its outcome; handles are exchanged
+        and peers are opened only when every rank got that far.  On any failure every rank releases what it holds and raises
+        PeerSetupError (the engine then falls back to NCCL on all ranks together)."""
         self.n, self.rank, self.world, self.device, self.backend = int(n), rank, world, device, backend
+        self.bufs, self.local = [], None
         fb, seg = self.FLAG_BYTES, self.n * 4
         n_grad = 1 if backend == "push" else 2
         slot = ((self.n // 4 + world - 1) // world) * 4 if backend == "push" else 0       # floats per staging slot
         stage_off = fb + (1 + n_grad) * seg
         nbytes = stage_off + world * slot * 4
         mc_base = 0
+
+        def agree(ok, what, err=None):
+            """all ranks succeeded?  (one all-reduce; every rank calls it at the same point whatever happened locally)"""
+            if world > 1:
+                t = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+                ok_all = bool(int(t.item()))
+            else:
+                ok_all = ok
+            if not ok_all:
+                self.close()
+                raise PeerSetupError(f"{backend}: {what} failed on {'this rank: ' + str(err) if not ok else 'a peer'}")
+
         if backend == "nvls":
-            import torch.distributed._symmetric_memory as symm_mem
-            self._symm = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
-            self._symm.zero_()
-            self._hdl = symm_mem.rendezvous(self._symm, group if group is not None else dist.group.WORLD)
-            mc_base = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
-            if mc_base == 0:
-                raise RuntimeError("symmetric memory has no multicast (NVLS) address on this system")
-            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
-            self.bufs = []
+            err = None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._symm = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
+                self._symm.zero_()
+            except Exception as e:   # noqa: BLE001
+                err = e
+            agree(err is None, "symmetric allocation", err)
+            try:
+                self._hdl = symm_mem.rendezvous(self._symm, group if group is not None else dist.group.WORLD)
+                mc_base = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+                if mc_base == 0:
+                    raise RuntimeError("symmetric memory has no multicast (NVLS) address on this system")
+                ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            except Exception as e:   # noqa: BLE001
+                err = e
+            agree(err is None, "rendezvous / multicast", err)
             flat = self._symm
             self.flags = flat[: fb // 4].view(torch.int32)[: _lib.XFLAG_WORDS]
             self.param = flat[fb // 4 : fb // 4 + self.n]
             self.grad = [flat[fb // 4 + (1 + k) * self.n : fb // 4 + (2 + k) * self.n] for k in (0, 1)]
             local_ptr = ptrs[rank]
         else:
-            self.local = _lib.peer_alloc(nbytes)
-            handles = [None] * world
+            err = None
+            try:                                           # stage 1: local allocation
+                self.local = _lib.peer_alloc(nbytes)
+            except Exception as e:   # noqa: BLE001
+                err = e
+            agree(err is None, "peer_alloc", err)
+            handles = [None] * world                       # stage 2: handle exchange (every rank is here)
             if world > 1:
                 dist.all_gather_object(handles, self.local.handle, group=group)
-            self.bufs = [self.local if w == rank else _lib.peer_open(handles[w], nbytes) for w in range(world)]
+            try:                                           # stage 3: map the peers
+                for w in range(world):
+                    if w == rank:
+                        self.bufs.append(self.local)
+                    else:
+                        if os.environ.get("NAFB_TEST_FAIL_PEER_OPEN") == str(rank):
+                            raise RuntimeError("injected peer_open failure (NAFB_TEST_FAIL_PEER_OPEN)")
+                        self.bufs.append(_lib.peer_open(handles[w], nbytes))
+            except Exception as e:   # noqa: BLE001
+                err = e
+            agree(err is None, "peer_open", err)
             ptrs = [b.ptr for b in self.bufs]
             self.flags = self.local.tensor(0, _lib.XFLAG_WORDS, torch.int32, device)
             self.param = self.local.tensor(fb, self.n, torch.float32, device)
@@ -163,17 +209,35 @@ class PeerExchange:
             torch.cuda.synchronize(device)
             dist.barrier(group=group)   # every rank has mapped every buffer before anybody launches
 
+    def reset_flags(self, group=None):
+        """Zero the epoch flags of every rank (collective).  Needed whenever the optimizer step -- the synchronisation epoch --
+        moves BACKWARDS (a checkpoint rollback): stale flags of later epochs would satisfy the kernel's waits at once."""
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)
+        self.flags.zero_()
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)
+
     def step(self, par, lr, betas, eps, step, stream):
-        _lib.check(_lib.lib().nafb_adam_exchange_step(ctypes.byref(self.desc[par]), lr, betas[0], betas[1], eps, step, 1.0 / self.world, stream))
+        # grad_scale 1: the step's loss is the SUM of the ranks' chunked losses -- the reference's own rule (train.py:69-127 adds the
+        # chunk means), so W ranks equal one GPU working on the concatenated batch with the same chunk boundaries
+        _lib.check(_lib.lib().nafb_adam_exchange_step(ctypes.byref(self.desc[par]), lr, betas[0], betas[1], eps, step, 1.0, stream))
 
     def error_word(self) -> int:
         """0, or 1 + index of the peer flag a bounded spin gave up on (synchronises the stream)."""
         return int(self.flags[_lib.XFLAG_ERROR].item())
 
     def close(self):
+        """Release every mapping and the local allocation (idempotent)."""
         for b in self.bufs:
-            if b is not getattr(self, "local", None):
+            if b is not self.local:
                 b.release()
+        self.bufs = []
+        if self.local is not None:
+            self.local.release()
+            self.local = None
 
 
 def _stage(dst: torch.Tensor, src: torch.Tensor, dtype):
@@ -233,6 +297,10 @@ class NAFEngine:
         self._eager_runs = {}
         self._host_seq = 0
         self._static = {}
+        # backward workspace of THIS engine (per-CTA partial MLP gradients + the words of the kernel's grid barrier): never shared
+        # with another engine or stream, zero-filled once
+        from .fused import new_workspace
+        self._bwd_ws = new_workspace(self.meta.mlp(self.mlp_params), self.device)
 
     # ------------------------------------------------------------------ flat parameter vector
     def _flatten(self, exchange="auto"):
@@ -250,25 +318,17 @@ class NAFEngine:
         # CUDA IPC, else NCCL.  Every rank must take the same decision, hence the all-reduce of the outcome.
         candidates = {"auto": ["push"] if self.world_size > 1 else [], "push": ["push"], "nvls": ["nvls"], "peer": ["ipc"], "nccl": []}[exchange]
         for backend in candidates:
-            ok = 1
             try:
                 if self.world_size > _lib.NAFB_MAX_RANKS:
-                    raise RuntimeError(f"peer exchange supports up to {_lib.NAFB_MAX_RANKS} ranks")
+                    raise PeerSetupError(f"peer exchange supports up to {_lib.NAFB_MAX_RANKS} ranks")      # same decision on every rank
                 if backend == "nvls" and self.world_size == 1:
-                    raise RuntimeError("NVLS needs more than one rank")
+                    raise PeerSetupError("NVLS needs more than one rank")
                 with torch.cuda.device(self.device):
                     self.px = PeerExchange(n, self.device, self.pg, self.rank, self.world_size, backend)
-            except Exception as e:  # not available here (container / topology)
+            except PeerSetupError as e:   # raised on every rank together (PeerExchange agrees on each stage's outcome)
                 if self.world_size == 1:
                     raise
-                self._peer_error, ok, self.px = f"{backend}: {e}", 0, None
-            if self.world_size > 1:
-                t = torch.tensor([ok], device=self.device, dtype=torch.int32)
-                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.pg)
-                if int(t.item()) == 0:
-                    if self.px is not None:
-                        self.px.close()
-                    self.px = None
+                self._peer_error, self.px = str(e), None
             if self.px is not None:
                 break
         if self.px is None and exchange in ("push", "nvls", "peer"):
@@ -316,7 +376,7 @@ class NAFEngine:
         seed ^= (0x9E3779B97F4A7C15 * (self.rank + 1)) & 0xFFFFFFFFFFFFFFFF      # every rank draws its own jitter
         st = np.zeros(_lib.STATE_WORDS, dtype=np.uint32)
         st[_lib.STATE_SEED_LO], st[_lib.STATE_SEED_HI] = seed & 0xFFFFFFFF, seed >> 32
-        st[_lib.STATE_LR] = np.float32(self._lr).view(np.uint32)
+        st[_lib.STATE_LR : _lib.STATE_LR + 2] = np.array([self._lr], dtype=np.float64).view(np.uint32)
         self.state = torch.from_numpy(st.view(np.int32)).to(self.device)
         if self.px is not None:
             for x in self.px.desc:
@@ -331,7 +391,7 @@ class NAFEngine:
         """Learning rate (follow a scheduler by assignment); mirrored into the device state the kernels read."""
         self._lr = float(value)
         if getattr(self, "state", None) is not None:
-            self.state[_lib.STATE_LR : _lib.STATE_LR + 1] = torch.tensor([np.float32(self._lr).view(np.int32)], dtype=torch.int32)
+            self.state[_lib.STATE_LR : _lib.STATE_LR + 2] = torch.tensor(_lib.lr_words(self._lr), dtype=torch.int32)
 
     def _set_step(self, step):
         self.step_count = int(step)
@@ -367,15 +427,26 @@ class NAFEngine:
         explicit = self.perturb and t_rand is not None
         smp = self._ray_sampler(rays, pixels, t_rand if explicit else None)
         st = _lib.stream_ptr()
-        with tm("density_fwd"):
-            _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, None, _lib.ptr(acc),
-                                               None, None, None, _lib.ptr(stash), st))
         chunk = int(self.loss_chunk or 0)
-        with tm("mse_loss"):
-            _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), 1, st))
+        if stash is not None:
+            # tensor-core configuration: ONE launch = ray generation + sampling + gather + MLP + ray integral, and its last CTA
+            # evaluates the masked chunk-wise MSE and d loss / d acc (nafb_density_forward_loss)
+            tail = _lib.LossTail(target=projs.data_ptr(), mask=mask.data_ptr() if mask is not None else None, chunk=chunk, gscale=1.0,
+                                 loss_out=loss_out.data_ptr(), dacc=dacc.data_ptr(), zero_pred=1,
+                                 ticket=self.state.data_ptr() + 4 * _lib.STATE_TICKET_FWD)
+            with tm("density_fwd_loss"):
+                _lib.check(L_.nafb_density_forward_loss(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.ptr(acc), None, _lib.ptr(stash),
+                                                        ctypes.byref(tail), st))
+        else:
+            with tm("density_fwd"):
+                _lib.check(L_.nafb_density_forward(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.SRC_RAYS, None, _lib.ptr(acc),
+                                                   None, None, None, None, st))
+            with tm("mse_loss"):
+                _lib.check(L_.nafb_mse_loss(_lib.ptr(acc), _lib.ptr(projs), _lib.ptr(mask), N, chunk, 1.0, _lib.ptr(loss_out), _lib.ptr(dacc), 1, st))
         with tm("density_bwd"):
             gv = self._grad_views[par]
-            density_backward(self.meta, self.table, self.mlp_params, dacc, gv[0], gv[1:], sampler=smp, n_points=N * self.n_samples, stash=stash)
+            density_backward(self.meta, self.table, self.mlp_params, dacc, gv[0], gv[1:], sampler=smp, n_points=N * self.n_samples, stash=stash,
+                             workspace=self._bwd_ws)
 
     def _optimizer_kernel(self, par, timer=None):
         """Peer mode: the fused exchange kernel.  Otherwise the dense Adam kernel.  Both take step / lr from the device state
@@ -389,7 +460,7 @@ class NAFEngine:
         with tm("adam"):
             _lib.check(L_.nafb_adam_step_dev(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
                                              _lib.ptr(self.exp_avg_sq), self.n_params, self.betas[0], self.betas[1], self.eps,
-                                             1.0 / self.world_size, 1, _lib.ptr(self.state), _lib.stream_ptr()))
+                                             1.0, 1, _lib.ptr(self.state), _lib.stream_ptr()))
 
     def _whole_step(self, s, par, timer=None, t_rand=None, with_optimizer=True, use_pixels=False, loss_out=None):
         self._step_kernels(None if use_pixels else s["rays"], s["projs"], s["mask"], t_rand, s["loss"] if loss_out is None else loss_out,
@@ -404,9 +475,11 @@ class NAFEngine:
                 parallel.allreduce_sum_(self.flat_grad, self.pg)
         self._optimizer_kernel(par, timer)
 
-    # kernels of this library launched by one train_step (density_fwd, mse_loss, density_bwd, adam / adam_exchange; the fp32 SIMT
-    # mode of the MLP adds a reduce_partials launch)
-    LAUNCHES_PER_STEP = 4
+    @property
+    def launches_per_step(self):
+        """Kernels of this library launched by one train_step: density_fwd_loss, density_bwd, adam / adam_exchange in the
+        tensor-core configuration; the fp32 SIMT arithmetic runs density_fwd, mse_loss, density_bwd, reduce_partials, adam."""
+        return 3 if self.use_stash and stash_bytes(self.meta, self.table, self.mlp_params, 128) else 5
 
     def _load_inputs(self, s, rays, projs, mask, t_rand, pixels=None):
         """Inputs -> the static buffers the graph reads (device tensors, or pinned host tensors: one H2D copy each)."""
@@ -493,6 +566,41 @@ class NAFEngine:
             self.step_count += 1
         return s["loss"][0]
 
+    def train_step_sampled(self, sampler, n_rays: int):
+        """One optimisation step whose batch is DRAWN ON THE DEVICE (dataset.mask.PixelSampler; reference
+        src/dataset/tigre.py:354-382 + train.py:59-60,93-95): the draw kernel writes the pixels, projection values and mask bits of
+        the next projection straight into the buffers the fused step reads, and the whole iteration -- draw, forward + loss,
+        backward, optimizer -- is ONE CUDA graph with no per-step host input at all (needs set_geometry).  Returns the loss as a
+        0-dim device tensor."""
+        if getattr(self, "poses", None) is None:
+            raise RuntimeError("train_step_sampled needs NAFEngine.set_geometry(angles, geo) first")
+        N, with_mask = int(n_rays), sampler.mask is not None
+        s = self._get_static(N, with_mask)
+        with torch.cuda.device(self.device):
+            par = self._parity()
+            in_graph = not (self.world_size > 1 and self.px is None)
+
+            def body(with_optimizer):
+                sampler.draw_into(N, s["pixels"], s["projs"], s["mask"])
+                self._whole_step(s, par, None, None, with_optimizer=with_optimizer, use_pixels=True)
+
+            key = (N, with_mask, par, "sampled", id(sampler))
+            g = self._graphs.get(key)
+            if not self.use_cuda_graph or self._eager_runs.get(key, 0) < 1:
+                self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
+                body(True)
+            else:
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        body(in_graph)
+                    self._graphs[key] = g
+                g.replay()
+                if not in_graph:
+                    self._finish_step(par)
+            self.step_count += 1
+        return s["loss"][0]
+
     HOST_SLOTS = 3   # pinned staging slots of train_step_host: a step can be enqueued while the previous one is still running
 
     def train_step_host(self, projs, mask=None, pixels=None, rays=None, wait=True):
@@ -565,6 +673,20 @@ class NAFEngine:
         h["pending"] = PendingLoss(h["event"], h["loss_np"])
         return h["pending"].result() if wait else h["pending"]
 
+    def check_health(self):
+        """Raise if a kernel of a past step reported a failure it could not signal otherwise: the backward kernel's grid barrier
+        timed out (a CTA never became resident: the MLP gradients of that step are missing), or -- several GPUs -- a bounded
+        spin of the exchange kernel gave up on a peer (replicas have diverged).  Synchronises the stream; call it wherever the
+        host already waits (evaluation, checkpoints)."""
+        bad = int(self._bwd_ws[-64:].view(torch.int32)[2].item())
+        if bad:
+            raise RuntimeError("density_backward: the grid-wide barrier timed out (workspace shared between concurrent launches, or the "
+                               "grid was not resident); MLP gradients of at least one step were lost")
+        if self.px is not None:
+            w = self.px.error_word()
+            if w:
+                raise RuntimeError(f"gradient exchange: rank {self.rank} gave up waiting for flag word {w - 1} of a peer; replicas have diverged")
+
     # ------------------------------------------------------------------ inference
     @torch.no_grad()
     def render_projection(self, rays=None, t_rand=None, perturb=None, pixels=None):
@@ -588,15 +710,30 @@ class NAFEngine:
         return acc
 
     @torch.no_grad()
-    def eval_step(self, view: int, proj_gt: torch.Tensor, image_gt: torch.Tensor, n_voxel, s_half, perturb=None):
+    def render_view(self, view: int, H: int, W: int, perturb=None, shard: bool = True):
+        """Projection `view` rendered for every detector pixel (reference train.py:235-240: the rays of the chosen view in chunks of
+        n_rays through render()), rays generated in-kernel.  With several ranks and shard=True the H*W pixels are SPLIT over the
+        ranks (contiguous ranges, parallel.shard_range) and the line integrals all-gathered: every rank returns the whole [H,W]
+        image having rendered 1/W of it.  Collective when sharded."""
+        n = H * W
+        i0, i1 = parallel.shard_range(n, self.rank, self.world_size) if (shard and self.world_size > 1) else (0, n)
+        flat = torch.arange(i0, i1, device=self.device, dtype=torch.int64)
+        pixels = torch.stack([torch.full_like(flat, int(view)), flat // W, flat % W], dim=-1).to(torch.int32)
+        local = self.render_projection(pixels=pixels, perturb=perturb) if i1 > i0 else torch.zeros(0, device=self.device)
+        if shard and self.world_size > 1:
+            local = parallel.gather_shards(local, n, self.pg)
+        return local.reshape(H, W)
+
+    @torch.no_grad()
+    def eval_step(self, view: int, proj_gt: torch.Tensor, image_gt: torch.Tensor, n_voxel, s_half, perturb=None, shard: bool = True):
         """The reference's eval_step (train.py:220-286) without its host round trips: render projection `view` (every
-        detector pixel, rays generated in-kernel), query the whole volume, score both on the device.
+        detector pixel, rays generated in-kernel; split over the ranks and all-gathered when there are several), query the
+        whole volume, score both on the device.
         proj_gt [H,W], image_gt [n1,n2,n3].  Returns {"proj_mse", "proj_psnr", "psnr_3d", "ssim_3d", "projs_pred", "image_pred"}."""
         from .utils import get_mse, get_psnr, get_psnr_3d, get_ssim_3d
+        self.check_health()
         H, W = proj_gt.shape
-        row, col = torch.meshgrid(torch.arange(H, device=self.device), torch.arange(W, device=self.device), indexing="ij")
-        pixels = torch.stack([torch.full_like(row, int(view)), row, col], dim=-1).reshape(-1, 3).to(torch.int32)
-        projs_pred = self.render_projection(pixels=pixels, perturb=perturb).reshape(H, W)
+        projs_pred = self.render_view(view, H, W, perturb=perturb, shard=shard)
         image_pred = self.voxel_query(n_voxel, s_half)
         out = {"proj_mse": float(get_mse(projs_pred, proj_gt)), "proj_psnr": float(get_psnr(projs_pred, proj_gt)),
                "psnr_3d": get_psnr_3d(image_pred, image_gt), "projs_pred": projs_pred, "image_pred": image_pred}
@@ -633,16 +770,64 @@ class NAFEngine:
             dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.pg)   # slices are disjoint
         return full
 
+    def _param_slices(self):
+        """(parameter, offset, numel) of the module's parameters inside the flat vector, in net.parameters() order."""
+        params = [self.net.encoder.embeddings] + self.net.flat_params()
+        out, n = [], 2
+        for p in params:
+            out.append((p, n, p.numel()))
+            n += _round_up(p.numel(), 4)
+        return out
+
     def optimizer_state_dict(self):
-        return {"step": self.step_count, "exp_avg": self._full_state(self.exp_avg), "exp_avg_sq": self._full_state(self.exp_avg_sq),
-                "lr": self._lr}
+        """The optimizer state in the layout of ``torch.optim.Adam(net.parameters(), lr, betas).state_dict()`` -- what the reference
+        trainer stores under ckpt["optimizer"] (src/trainer.py:118-126) and restores with optimizer.load_state_dict (:60-70): per
+        parameter {"step", "exp_avg", "exp_avg_sq"} in net.parameters() order + "param_groups".  A ckpt.tar written by the
+        reference trainer resumes here and vice versa.
+        COLLECTIVE with a peer-memory exchange (each rank holds the moments of its slice only: they are all-gathered): call it on
+        EVERY rank, then let rank 0 save."""
+        self.check_health()
+        m, v = self._full_state(self.exp_avg), self._full_state(self.exp_avg_sq)
+        opt = torch.optim.Adam(list(self.net.parameters()), lr=self._lr, betas=self.betas, eps=self.eps)
+        if self.step_count > 0:
+            for p, o, n in self._param_slices():
+                opt.state[p] = {"step": torch.tensor(float(self.step_count)), "exp_avg": m[o:o + n].view_as(p).clone(),
+                                "exp_avg_sq": v[o:o + n].view_as(p).clone()}
+        return opt.state_dict()
 
     def load_optimizer_state_dict(self, sd):
+        """Accepts a torch.optim.Adam state_dict (the reference's ckpt["optimizer"]; int or tensor `step`) -- or the flat dict
+        {"step", "exp_avg", "exp_avg_sq", "lr"} of the first round.  Collective with a peer-memory exchange."""
+        if "param_groups" in sd:
+            slices = self._param_slices()
+            group = sd["param_groups"][0]
+            if len(group["params"]) != len(slices):
+                raise ValueError(f"optimizer state has {len(group['params'])} parameters, the network {len(slices)}")
+            m = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
+            v = torch.zeros_like(m)
+            step = 0
+            for pid, (p, o, n) in zip(group["params"], slices):
+                st = sd["state"].get(pid)
+                if st is None:
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state of parameter {pid} has shape {tuple(st['exp_avg'].shape)}, expected {tuple(p.shape)}")
+                m[o:o + n] = st["exp_avg"].reshape(-1).to(self.device, torch.float32)
+                v[o:o + n] = st["exp_avg_sq"].reshape(-1).to(self.device, torch.float32)
+                step = max(step, int(float(st["step"])))
+            sd = {"step": step, "exp_avg": m, "exp_avg_sq": v, "lr": float(group["lr"])}
+            self.betas = (float(group["betas"][0]), float(group["betas"][1]))
+            self.eps = float(group["eps"])
         self._set_step(sd["step"])
         i0, i1 = self.px.slice if self.px is not None else (0, self.n_params)
         self.exp_avg.copy_(sd["exp_avg"][i0:i1])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"][i0:i1])
         self.lr = float(sd.get("lr", self._lr))
-        if self.px is not None:   # the parity of step_count selects the gradient buffer: both must be clean
-            for g in self.flat_grads:
+        self._graphs.clear()        # betas / eps are kernel arguments of the captured launches
+        self._eager_runs.clear()
+        if self.px is not None:
+            for g in self.flat_grads:   # the parity of step_count selects the gradient buffer: both must be clean
                 g.zero_()
+            # the optimizer step doubles as the synchronisation epoch of the exchange kernel: after a rollback the flags of later
+            # epochs would satisfy its waits immediately -> clear them on every rank, between barriers
+            self.px.reset_flags(self.pg)

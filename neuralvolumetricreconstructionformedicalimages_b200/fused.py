@@ -18,6 +18,21 @@ from torch.autograd import Function
 from . import _lib
 
 
+# Arithmetic of the fused density kernels for networks that do not choose one themselves (NetMeta.arith is None):
+# _lib.ARITH_TC = tcgen05 tensor cores (bf16x3 split products, fp32 accumulation) where the configuration allows,
+# _lib.ARITH_SIMT = fp32 FMAs everywhere.  The choice travels WITH EVERY CALL (nafb_mlp.arith): the library keeps no mode.
+DEFAULT_ARITH = _lib.ARITH_TC
+
+
+def set_default_arithmetic(arith: int) -> int:
+    """Set the package-wide default (returns the previous one).  Per network: `net.fused_meta().arith = ...`."""
+    global DEFAULT_ARITH
+    if arith not in (_lib.ARITH_TC, _lib.ARITH_SIMT):
+        raise ValueError("arithmetic must be _lib.ARITH_TC (0) or _lib.ARITH_SIMT (1)")
+    prev, DEFAULT_ARITH = DEFAULT_ARITH, int(arith)
+    return prev
+
+
 class NetMeta:
     """Static description of a DensityNetwork for the kernels (shapes, skips, head, grid)."""
 
@@ -29,6 +44,7 @@ class NetMeta:
         self.head = head
         self.bound = float(bound)
         self.n_layers = int(n_layers)
+        self.arith = None   # None: follow fused.DEFAULT_ARITH at call time
 
     def fused_supported(self) -> bool:
         return (self.D == 3 and self.in_dim == 32 and self.hidden == 32 and self.out_dim == 1 and 2 <= self.n_layers <= _lib.NAFB_MAX_LAYERS
@@ -39,7 +55,8 @@ class NetMeta:
 
     def mlp(self, params):
         ws, bs = params[0::2], params[1::2]
-        return _lib.make_mlp(ws, bs, self.in_dim, self.hidden, self.out_dim, self.skips, self.head)
+        return _lib.make_mlp(ws, bs, self.in_dim, self.hidden, self.out_dim, self.skips, self.head,
+                             DEFAULT_ARITH if self.arith is None else self.arith)
 
     def sampler(self, **kw):
         s = _lib.Sampler()
@@ -58,13 +75,21 @@ _ws_cache = {}
 
 
 def _workspace(mlp_struct, device):
+    """Workspace of the autograd front-ends: one per (device, CUDA stream) -- launches on one stream are ordered, launches on
+    different streams must not share the grid-barrier words."""
     n = int(_lib.lib().nafb_density_backward_workspace_bytes(ctypes.byref(mlp_struct)))
-    key = (device, n)
+    key = (device, n, torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None:
         ws = torch.zeros(n, dtype=torch.uint8, device=device)   # zero-filled: it holds the words of the backward kernel's grid barrier
         _ws_cache[key] = ws
     return ws
+
+
+def new_workspace(mlp_struct, device):
+    """A private backward workspace (zero-filled): for callers that may have several backward launches in flight."""
+    n = int(_lib.lib().nafb_density_backward_workspace_bytes(ctypes.byref(mlp_struct)))
+    return torch.zeros(n, dtype=torch.uint8, device=device)
 
 
 def stash_bytes(meta: NetMeta, table, params, n_points: int) -> int:
@@ -119,7 +144,7 @@ def density_forward(meta: NetMeta, table, params, *, pts=None, rays=None, t_rand
 
 
 def density_backward(meta: NetMeta, table, params, dsig_or_dacc, grad_table, grad_params, *, pts=None, rays=None, t_rand=None,
-                     n_samples=0, perturb=False, stash=None, rng_state=None, sampler=None, n_points=None):
+                     n_samples=0, perturb=False, stash=None, rng_state=None, sampler=None, n_points=None, workspace=None):
     """Accumulates into grad_table / grad_params (list aligned with params; entries may be None).
     `stash` is what density_forward(want_stash=True) returned for the same points, or None.
     `sampler`: a ready nafb_sampler of the RAYS source (the engine passes the one its forward used) with `n_points`."""
@@ -138,7 +163,7 @@ def density_backward(meta: NetMeta, table, params, dsig_or_dacc, grad_table, gra
                            rng_state=rng_state.data_ptr() if (perturb and t_rand is None and rng_state is not None) else None,
                            n_rays=rays.shape[0], n_samples=n_samples, perturb=int(bool(perturb)))
         src = _lib.SRC_RAYS
-    ws = _workspace(mlp, dev)
+    ws = workspace if workspace is not None else _workspace(mlp, dev)
     if stash is not None:
         P = n_points if sampler is not None else (pts.shape[0] if pts is not None else rays.shape[0] * n_samples)
         if stash.numel() != int(L_.nafb_density_stash_bytes(ctypes.byref(grid), ctypes.byref(mlp), P)):

@@ -49,6 +49,7 @@ class DensityNetwork(nn.Module):
             return None
         meta = NetMeta(enc._offsets_np, enc.input_dim, enc.level_dim, enc.base_resolution, self.in_dim, self.hidden_dim,
                        self.layers[-1].out_features, [s for s in self.skips], self.last_activation, self.bound, len(self.layers))
+        meta.arith = getattr(self, "arith", None)   # None: fused.DEFAULT_ARITH; or _lib.ARITH_TC / _lib.ARITH_SIMT for this network
         return meta if meta.fused_supported() else None
 
     def flat_params(self):

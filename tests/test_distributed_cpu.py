@@ -2,10 +2,10 @@
 
 What is checked:
   * shard_range: disjoint, ordered, exact cover (rays across ranks, voxel slabs across ranks);
-  * the exchange step: per-rank gradients of the per-rank losses, summed with allreduce_sum_ and scaled by 1/world (what
-    NAFEngine hands to Adam), equal the single-process gradient of the mean of the two losses -- computed with the CPU
-    oracle network on real NAF rays, so the rule is checked on the actual loss (masked, chunked MSE of train.py:69-127);
-  * broadcast_ / replica_divergence / combined_loss.
+  * the exchange step: per-rank gradients of the per-rank losses, summed with allreduce_sum_ (what NAFEngine hands to Adam,
+    unscaled), equal the single-process gradient of the reference's chunked loss (train.py:69-127) on the CONCATENATED batch --
+    computed with the CPU oracle network on real NAF rays, masks included;
+  * broadcast_ / replica_divergence / combined_loss / gather_shards (the sharded evaluation render, train.py:235-240).
 The GPU kernels are not involved (tests/test_gpu_parity.py covers them); this is the N > 1 plumbing.
 """
 import os
@@ -69,7 +69,10 @@ def _rank_batch(rank, n_rays=48, S=16):
     return rays, projs, mask, t_rand, S
 
 
-def _loss(net, batch, chunk=20):
+CHUNK = 16            # divides the per-rank batch (48 rays), so the chunks of the concatenated batch are the ranks' chunks
+
+
+def _loss(net, batch, chunk=CHUNK):
     rays, projs, mask, t_rand, S = batch
     ret = naf.render(rays, net, S, True, t_rand=t_rand)
     return naf.chunked_masked_mse(ret["acc"], projs, mask, chunk)
@@ -96,9 +99,14 @@ def _worker(rank, port, out_dir):
         loss = _loss(net, _rank_batch(rank))
         loss.backward()
         flat_g = _flat([p.grad for p in net.parameters()]).clone()
-        parallel.allreduce_sum_(flat_g)
-        flat_g *= 1.0 / WORLD                            # grad_scale of nafb_adam_step
+        parallel.allreduce_sum_(flat_g)                  # handed to Adam unscaled (grad_scale 1)
         mean_loss = parallel.combined_loss(loss)
+        # sharded evaluation render: every rank holds its shard of a 37-element "acc", all ranks get the whole
+        j0, j1 = parallel.shard_range(37, rank, WORLD)
+        whole = parallel.gather_shards(torch.arange(j0, j1, dtype=torch.float32) * 2.0, 37)
+        assert torch.equal(whole, torch.arange(37, dtype=torch.float32) * 2.0)
+        whole2 = parallel.gather_shards(torch.arange(j0, j1)[:, None].repeat(1, 3), 37)
+        assert whole2.shape == (37, 3) and torch.equal(whole2[:, 1], torch.arange(37))
         # voxel slabs: every rank contributes its slab, the union is the whole lattice
         n1 = 7
         i0, i1 = parallel.shard_range(n1, rank, WORLD)
@@ -117,10 +125,13 @@ def test_two_rank_gradient_exchange_equals_single_process(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
     got = torch.load(os.path.join(str(tmp_path), "r0.pt"))
-    # single process: mean of the two per-rank losses on the same (rank-0) parameters
+    # single process: the reference's chunked loss on the concatenated batch, same (rank-0) parameters
     net = _small_net(seed=0)
     np.testing.assert_array_equal(got["param"].numpy(), _flat([p.detach() for p in net.parameters()]).numpy())
-    total = sum(_loss(net, _rank_batch(r)) for r in range(WORLD)) / WORLD
+    batches = [_rank_batch(r) for r in range(WORLD)]
+    concat = tuple(torch.cat([b[k] for b in batches], 0) for k in range(4)) + (batches[0][4],)
+    total = _loss(net, concat)
+    np.testing.assert_allclose(total.item(), sum(_loss(net, b).item() for b in batches), rtol=1e-6)
     total.backward()
     ref = _flat([p.grad for p in net.parameters()])
     np.testing.assert_allclose(got["loss"].item(), total.item(), rtol=1e-6)

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 def test_umma_selftest():
     from neuralvolumetricreconstructionformedicalimages_b200 import _lib
-    L_ = _lib.lib()
+    L_ = _lib.diag_lib()   # diagnostics live outside the product library (include/nafb200_diag.h)
     rng = np.random.default_rng(0)
     A = rng.normal(size=(128, 128)).astype(np.float32)
     X = rng.normal(size=(128, 32)).astype(np.float32)
@@ -18,7 +18,7 @@ def test_umma_selftest():
     D1 = torch.full((128, 32), float("nan"), device="cuda")
     D2 = torch.full((128, 64), float("nan"), device="cuda")
     D3 = torch.full((128, 32), float("nan"), device="cuda")
-    _lib.check(L_.nafb_selftest_umma(_lib.ptr(dA), _lib.ptr(dX), _lib.ptr(dW), _lib.ptr(D1), _lib.ptr(D2), _lib.ptr(D3), _lib.stream_ptr()))
+    assert 0 == (L_.nafb_selftest_umma(_lib.ptr(dA), _lib.ptr(dX), _lib.ptr(dW), _lib.ptr(D1), _lib.ptr(D2), _lib.ptr(D3), _lib.stream_ptr()))
     torch.cuda.synchronize()
     A64, X64, W64 = A.astype(np.float64), X.astype(np.float64), W.astype(np.float64)
     R1 = A64[:, :32] @ W64[:, :32].T

@@ -115,16 +115,22 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == _lib.exported_symbols()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.nafb_abi_version() == 8
+    assert L.nafb_abi_version() == 9
+    # the diagnostics library exports what include/nafb200_diag.h declares, and the product library does not carry them
+    dh = open(os.path.join(ROOT, "include", "nafb200_diag.h")).read()
+    D = _lib.diag_lib()
+    for name in sorted(set(re.findall(r"\b(nafb_[a-z0-9_]+)\s*\(", dh))):
+        assert hasattr(D, name), name
+        assert not hasattr(L, name), name
     # struct layouts agree with the C header (sizes computed by the C compiler)
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "nafb200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(nafb_grid), sizeof(nafb_mlp), sizeof(nafb_mlp_grads), sizeof(nafb_sampler), sizeof(nafb_exchange));}'
+    src = '#include <stdio.h>\n#include "nafb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(nafb_grid), sizeof(nafb_mlp), sizeof(nafb_mlp_grads), sizeof(nafb_sampler), sizeof(nafb_exchange), sizeof(nafb_loss_tail));}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
-    assert sizes == [ctypes.sizeof(_lib.Grid), ctypes.sizeof(_lib.Mlp), ctypes.sizeof(_lib.MlpGrads), ctypes.sizeof(_lib.Sampler), ctypes.sizeof(_lib.Exchange)]
+    assert sizes == [ctypes.sizeof(_lib.Grid), ctypes.sizeof(_lib.Mlp), ctypes.sizeof(_lib.MlpGrads), ctypes.sizeof(_lib.Sampler), ctypes.sizeof(_lib.Exchange), ctypes.sizeof(_lib.LossTail)]
     # argument validation happens before any launch: safe to exercise without a GPU
     assert L.nafb_adam_step(None, None, None, None, 4, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, 1, None) == _lib.ERR_INVALID
     assert b"null pointer" in L.nafb_last_error()
@@ -134,36 +140,15 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.nafb_last_error() == b"GridEncoding: C must be 1, 2, 4, or 8."
 
 
-def test_ptycho_mask_and_pixel_sampler(golden):
-    """get_ptycho_mask against the reference's output (util.py:196-205); PixelSampler draws valid pixels without replacement."""
+def test_pixel_sampler_and_mask_need_a_gpu():
+    """The mask / pixel selection run in CUDA kernels (csrc/select.cu); like every operator of the package they refuse CPU
+    tensors instead of falling back.  (The oracle's restatement of the mask is pinned to the reference's output in
+    test_oracle_golden.py; the kernels are compared with it in tests/test_gpu_select.py.)"""
     from neuralvolumetricreconstructionformedicalimages_b200.dataset.mask import PixelSampler, get_ptycho_mask
-    fx = golden("geometry.npz")
-    m = get_ptycho_mask(torch.from_numpy(fx["mask_in"].copy()), 0.007).numpy()
-    assert np.array_equal(m, fx["mask_out"])
-    rng = np.random.default_rng(4)
-    projs = torch.from_numpy(rng.uniform(0, 1, (3, 12, 17)).astype(np.float32))
-    projs[1, :4] = 0.0                                    # tigre.py:356: zero pixels are never drawn
-    full = torch.from_numpy(np.stack([fx["mask_in"]] * 3))
-    ps = PixelSampler(projs, full, 0.007)
-    assert np.array_equal(ps.mask[0].numpy().astype(bool), fx["mask_out"])
-    g = torch.Generator().manual_seed(0)
-    pix, pr, mk = ps.draw(1, 50, g)
-    assert pix.shape == (50, 3) and pix.dtype == torch.int32 and int(pix[:, 0].min()) == 1 and int(pix[:, 0].max()) == 1
-    flat = (pix[:, 1].long() * 17 + pix[:, 2].long()).numpy()
-    assert len(np.unique(flat)) == 50 and int(pix[:, 1].min()) >= 4      # no replacement, rows 0..3 (zero projection) excluded
-    assert torch.equal(pr, projs[1].reshape(-1)[flat]) and torch.equal(mk, ps.mask[1].reshape(-1)[flat])
-    with pytest.raises(ValueError):
-        ps.draw(1, 12 * 17, g)
-    # a whole epoch at once
-    pe, pre, mke = ps.draw_epoch(40, g, projections=[2, 0, 1])
-    assert pe.shape == (3, 40, 3) and pre.shape == (3, 40) and mke.shape == (3, 40) and pe[:, 0, 0].tolist() == [2, 0, 1]
-    for k, pj in enumerate([2, 0, 1]):
-        fl = (pe[k, :, 1].long() * 17 + pe[k, :, 2].long()).numpy()
-        assert len(np.unique(fl)) == 40
-        assert torch.equal(pre[k], projs[pj].reshape(-1)[fl]) and torch.equal(mke[k], ps.mask[pj].reshape(-1)[fl])
-    assert int(pe[2, :, 1].min()) >= 4                                    # projection 1: rows 0..3 never drawn
-    with pytest.raises(ValueError):
-        ps.draw_epoch(12 * 17 - 10, g)
+    with pytest.raises(RuntimeError):
+        get_ptycho_mask(torch.zeros(4, 4, dtype=torch.complex64), 0.007)
+    with pytest.raises(RuntimeError):
+        PixelSampler(torch.ones(2, 4, 4))
 
 
 def test_pose_table_and_detector_fields(golden):
