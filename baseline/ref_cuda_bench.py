@@ -71,5 +71,71 @@ def main():
                           "workload": bench.WORKLOAD}), flush=True)
 
 
+def extra():
+    """REF_EXTRA=1: the reference's CUDA build on the two other single-GPU configurations of BASELINE.json: one large-batch
+    training step (65 536 rays x 384 samples in one render() call) and the 512^3 voxel query (run_network over the materialised
+    coordinate tensor in chunks of netchunk = 409 600, train.py:246-250)."""
+    sys.path.insert(0, ROOT)
+    from baseline.ref_loader import import_reference
+    get_encoder, get_network, render, calc_mse_loss = import_reference("cuda")
+    import bench
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
+    sys.path.insert(0, REF)
+    from src.render import run_network
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
+    net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    # ---- large batch
+    data = G.chest50_like(256, 256, 50)
+    geo = G.ConeGeometry(data)
+    rays_all = G.rays_with_near_far(data["angles"][:4], geo, dev).reshape(-1, 8)
+    N, S = 65536, 384
+    gen = torch.Generator(device=dev).manual_seed(1)
+    times = []
+    for it in range(3):
+        rays = rays_all[torch.randint(0, rays_all.shape[0], (N,), device=dev, generator=gen)]
+        projs = torch.rand(N, device=dev, generator=gen) * 0.05
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        opt.zero_grad()
+        loss = {"loss": 0.0}
+        ret = render(rays, net, None, n_samples=S, n_fine=0, perturb=True, netchunk=409600, raw_noise_std=0.0)
+        calc_mse_loss(loss, projs, ret["acc"])
+        loss["loss"].backward()
+        opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+        del ret, loss
+    ms = float(np.median(times[1:]))
+    print(json.dumps({"impl": "reference_cuda", "variant": "large_batch", "ms_per_step": ms, "value": N * S / (ms * 1e-3), "unit": "samples/s",
+                      "workload": "65536 rays x 384 samples, one render() call per step"}), flush=True)
+    opt.zero_grad(set_to_none=True)
+    torch.cuda.empty_cache()
+    # ---- 512^3 voxel query
+    n = 512
+    s = (n * 0.001) / 2 - 0.001 / 2
+    lin = torch.from_numpy(np.linspace(-s, s, n)).to(dev)
+    vox = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1).to(torch.float32)          # [n,n,n,3], 1.6 GB (tigre.py:388-400)
+    times = []
+    with torch.no_grad():
+        for it in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            img = run_network(vox, net, 409600)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+            del img
+    print(json.dumps({"impl": "reference_cuda", "variant": "voxel_query_512", "ms": float(times[-1]), "value": n ** 3 / (times[-1] * 1e-3),
+                      "unit": "voxels/s", "workload": "run_network over the 512^3 lattice, netchunk 409600"}), flush=True)
+
+
 if __name__ == "__main__":
     main()
+    if os.environ.get("REF_EXTRA") == "1":
+        extra()

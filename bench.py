@@ -47,25 +47,38 @@ def measured_peaks():
     return dict(hbm=6650.0, tensor=1590.0, source="fallback")
 
 
-def ncu_dram_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel from the newest committed `ncu --set full`
-    summary under profiles/ (None when there is none)."""
+def ncu_summary(kernel):
+    """Metrics of the newest committed `ncu --set full` summary of a kernel under profiles/ (scripts/ncu_summary.py output):
+    {"file": ..., metric name: value in base units} or None."""
     import glob
     import re
-    pat = {"density_bwd": "*density_bwd*_full.txt", "density_fwd": "*density_fwd*_full.txt", "adam": "*adam*_full.txt"}.get(kernel)
+    pat = {"density_bwd": "*density_bwd*_full.txt", "density_fwd": "*density_fwd*_full.txt", "density_fwd_loss": "*density_fwd*_full.txt",
+           "adam": "*adam*_full.txt", "voxel_query": "*voxel*_full.txt"}.get(kernel)
     if not pat:
         return None
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pat)))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pat)), key=lambda f: (os.path.basename(f).split("_")[0], f))
     if not files:
         return None
-    total, unit_mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    found = 0
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0}
+    out = {"file": os.path.relpath(files[-1], ROOT)}
     for line in open(files[-1]):
-        m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
-        if m:
-            total += float(m.group(2)) * unit_mult.get(m.group(3), 1.0)
-            found += 1
-    return {"bytes_per_launch": total, "source": os.path.relpath(files[-1], ROOT)} if found == 2 else None
+        m = re.match(r"([a-z0-9_.]+)\s+([0-9.eE+-]+)\s*([A-Za-z/%]*)", line)
+        if m and m.group(1) not in out:
+            out[m.group(1)] = float(m.group(2)) * mult.get(m.group(3), 1.0)
+    return out
+
+
+def ncu_dram_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel from its committed ncu summary (None when absent)."""
+    d = ncu_summary(kernel)
+    if not d or "dram__bytes_read.sum" not in d or "dram__bytes_write.sum" not in d:
+        return None
+    return {"bytes_per_launch": d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"], "source": d["file"]}
+
+
+# measured L2-resident random-access rates of this pool's B200 (scripts/microbench.py -> profiles/r1_microbench_l2_rates.json):
+# what bounds the encoder's gather (address-divergent 8-byte loads) and scatter (8 / 16-byte float reductions), in G operations / s
+L2_GATHER_GOPS, L2_RED_GOPS = 263.5, 184.0
 
 
 class ClockSampler(threading.Thread):
@@ -215,6 +228,47 @@ def cpu_reference_run(steps, warmup, n_rays=N_RAYS):
                 n_rays=n_rays, kind=kind)
 
 
+def cpu_extra_baselines():
+    """Bounded CPU samples (host cores of this box) of the two other single-GPU workloads, through the same reference code as
+    cpu_reference_run: one training step of 4 096 rays x 384 samples (large batch is 16x that), and the voxel query on 2^18 voxels of
+    the 512^3 lattice (the query is 512x that)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    out = {}
+    try:
+        global N_SAMPLES
+        keep = N_SAMPLES
+        N_SAMPLES = 384
+        try:
+            r = cpu_reference_run(steps=2, warmup=1, n_rays=4096)
+        finally:
+            N_SAMPLES = keep
+        out["large_batch"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                              "sample": "2 timed steps of 4096 rays x 384 samples after 1 warm-up (1/16 of the large-batch step)"}
+    except Exception as e:   # noqa: BLE001
+        out["large_batch"] = {"unavailable": str(e)[:200]}
+    try:
+        from oracle import hashgrid as oh
+        from oracle import naf
+        torch.manual_seed(0)
+        enc = oh.OracleHashEncoder(3, 16, 2, 16, 19, use_ref=False, normalise="mul_recip")
+        net = naf.OracleDensityNetwork(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid")
+        n, m = 512, 64
+        s = (n * 0.001) / 2 - 0.001 / 2
+        lin = np.linspace(-s, s, n)
+        xyz = np.stack(np.meshgrid(lin[:m], lin[:m], lin[:m], indexing="ij"), -1).astype(np.float32).reshape(-1, 3)
+        with torch.no_grad():
+            naf.run_network(torch.from_numpy(xyz[:65536]), net, 409600)
+            t0 = time.perf_counter()
+            naf.run_network(torch.from_numpy(xyz), net, 409600)
+            dt = time.perf_counter() - t0
+        out["voxel_query_512"] = {"value": xyz.shape[0] / dt, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "port",
+                                  "ms_for_512_cubed": 1e3 * dt * (n ** 3) / xyz.shape[0],
+                                  "sample": "64^3 voxels of the 512^3 lattice (1/512 of the query) through the oracle (C hash grid with OpenMP + torch-CPU MLP)"}
+    except Exception as e:   # noqa: BLE001
+        out["voxel_query_512"] = {"unavailable": str(e)[:200]}
+    return out
+
+
 def reference_cuda_numbers():
     """The reference's own CUDA build timed on this GPU (baseline/ref_cuda_bench.py in a subprocess, ~2 s), when it is staged
     under baseline/_ref: the denominator of BASELINE.json's ">= 20x the reference's CUDA build" target, reported next to our
@@ -225,16 +279,17 @@ def reference_cuda_numbers():
         return None
     try:
         r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=300, cwd=ROOT,
-                           env=dict(os.environ, REF_STEPS="20", REF_WARMUP="5"))
+                           env=dict(os.environ, REF_STEPS="20", REF_WARMUP="5", REF_EXTRA="1"))
         out = {}
         for l in r.stdout.splitlines():
             if l.startswith("{"):
                 d = json.loads(l)
-                out[d["variant"]] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"]}
+                out[d["variant"]] = {k: d[k] for k in ("value", "unit", "ms_per_step", "ms") if k in d}
         if not out:
             return None
         out["note"] = ("the reference's render / DensityNetwork / HashEncoder (its CUDA extension, 2-line compile fix) / calc_mse_loss + "
-                       "torch.optim.Adam on the same workload: 'chunked' = train.py's 200-ray chunk loop, 'one_call' = one render() per step")
+                       "torch.optim.Adam on the same workload: 'chunked' = train.py's 200-ray chunk loop, 'one_call' = one render() per step; "
+                       "'large_batch' = one 65536 x 384 step, 'voxel_query_512' = run_network over the 512^3 lattice")
         return out
     except Exception:
         return None
@@ -341,9 +396,27 @@ def extra_workloads(device, world, rank):
     rb, pb, mb = batches(rays_all, 65536, 3)
     ms, loss = _time_steps(eng, rb, pb, mb, 4, 4, world)    # 4 warm-up steps: eager + graph capture for both gradient parities
     pts = 65536 * 384
+    pts = 65536 * 384
     out["large_batch"] = {"workload": "65536 rays x 384 samples per step per GPU, 256^3 volume, cone beam, one MSE chunk", "ms_per_step": ms,
                           "value": world * pts / (ms * 1e-3), "unit": "samples/s", "loss": loss,
                           "stash_gb": (eng._static[(65536, True)]["stash"].numel() / 1e9) if eng._static[(65536, True)]["stash"] is not None else 0.0}
+    # per-kernel times of the same step (instrumented eager pass) and the roofline of its dominant kernel
+    from neuralvolumetricreconstructionformedicalimages_b200.engine import EventTimer
+    tm = EventTimer()
+    eng.profiled_step(rb[0], pb[0], mb[0], None, EventTimer())
+    for i in range(2):
+        eng.profiled_step(rb[i % 3], pb[i % 3], mb[i % 3], None, tm)
+    torch.cuda.synchronize()
+    prof = {k: v[0] for k, v in tm.summary().items()}
+    out["large_batch"]["kernels_ms"] = prof
+    dom = max(prof, key=prof.get)
+    out["large_batch"]["roofline"] = {
+        "kernel": dom, "bound": "hbm", "achieved": TABLE_BYTES_PER_POINT * pts / (prof[dom] * 1e-3) / 1e9, "peak": measured_peaks()["hbm"], "unit": "GB/s",
+        "frac": TABLE_BYTES_PER_POINT * pts / (prof[dom] * 1e-3) / 1e9 / measured_peaks()["hbm"], "traffic": None,
+        "note": "algorithmic bytes = 1024 B/point of table entries reduced (backward) or gathered (forward); the table is L2-resident, the "
+                "limiter is the L2 operation rate: see `limiter`",
+        "limiter": {"bound": "l2_atomic" if "bwd" in dom else "l1tex_gather", "ops_per_point_upper_bound": 128,
+                    "achieved_gops_upper_bound": 128 * pts / (prof[dom] * 1e-3) / 1e9, "peak_gops": L2_RED_GOPS if "bwd" in dom else L2_GATHER_GOPS}}
     del rays_all, rb, pb, mb
     # ---- 512^3 voxel query, slabs of the outermost index per rank (no collective)
     n = 512
@@ -366,8 +439,24 @@ def extra_workloads(device, world, rank):
     t = torch.tensor([e0.elapsed_time(e1) / reps], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    vq_ms = float(t[0])
+    vox_per_rank = (i1 - i0) * n * n
+    gbs = TABLE_BYTES_PER_POINT * vox_per_rank / (vq_ms * 1e-3) / 1e9
+    nc = ncu_summary("voxel_query")
     out["voxel_query_512"] = {"workload": f"forward-only fused encode+MLP over the 512^3 lattice, outermost-index slabs over {world} GPU(s), fp32 output",
-                              "ms": float(t[0]), "value": n ** 3 / (float(t[0]) * 1e-3), "unit": "voxels/s", "mean_sigma": float(vol.mean().item())}
+                              "ms": vq_ms, "value": n ** 3 / (vq_ms * 1e-3), "unit": "voxels/s", "mean_sigma": float(vol.mean().item()),
+                              "roofline": {"kernel": "k_density_fwd_tc<VOXELS>", "bound": "hbm", "achieved": gbs, "peak": measured_peaks()["hbm"],
+                                           "unit": "GB/s", "frac": gbs / measured_peaks()["hbm"],
+                                           "traffic": (nc["dram__bytes_read.sum"] + nc["dram__bytes_write.sum"]) if nc and "dram__bytes_read.sum" in nc else None,
+                                           "traffic_source": (nc["file"] + " (128^3 query: scale by 64)") if nc else None,
+                                           "algorithmic_bytes_per_launch": TABLE_BYTES_PER_POINT * vox_per_rank + 4 * vox_per_rank,
+                                           "note": "1024 B of table entries gathered per voxel (+ 4 B written); the 57 MB table is L2-resident, so the "
+                                                   "applicable limit is the address-divergent load rate of the L1TEX / L2 path: see `limiter`",
+                                           "limiter": {"bound": "l1tex_gather", "achieved_gops_upper_bound": 128 * vox_per_rank / (vq_ms * 1e-3) / 1e9,
+                                                       "peak_gops": L2_GATHER_GOPS,
+                                                       "note": "128 corner loads per voxel before x-neighbour pair merging and L1 hits (a 4x4x8 block of "
+                                                               "the lattice per tile shares sectors); the random-access micro-benchmark is not a ceiling "
+                                                               "for spatially coherent points"}}}
     del eng, vol
     torch.cuda.empty_cache()
     return out
@@ -504,6 +593,16 @@ def main():
 
     extra = None if args.no_extra else extra_workloads(device, world, rank)
 
+    # ---------------- N > 1: are the replicas still identical, did a bounded spin of the exchange kernel give up?  (collective)
+    from neuralvolumetricreconstructionformedicalimages_b200 import parallel
+    torch.cuda.synchronize()
+    replica_div = parallel.replica_divergence(eng.flat_param, eng.pg)
+    err_word = torch.tensor([eng.px.error_word() if eng.px is not None else 0], device=device, dtype=torch.int32)
+    if world > 1:
+        dist.all_reduce(err_word, op=dist.ReduceOp.MAX)
+    eng.check_health()
+    loss_all = float(parallel.combined_loss(loss, eng.pg).item())
+
     # ---------------- reduce over ranks (max time)
     t = torch.tensor([ms, e2e_wall_ms, piped_wall_ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -517,13 +616,11 @@ def main():
         peaks = measured_peaks()
         step_sum = sum(v[0] for v in prof.values())
         kernels = {}
-        # algorithmic work per launch: table bytes gathered / reduced + the 128 B/point
-        # encoding stash, MLP flops, optimizer bytes
-        STASH = 128
+        # algorithmic work per launch: table bytes gathered / reduced, MLP flops, optimizer bytes
         algo = {
-            "density_fwd": (FLOP_FWD_PER_POINT * pts_step, (TABLE_BYTES_PER_POINT + STASH) * pts_step),
-            "density_fwd_loss": (FLOP_FWD_PER_POINT * pts_step, (TABLE_BYTES_PER_POINT + STASH) * pts_step),
-            "density_bwd": (FLOP_FWDBWD_PER_POINT * pts_step, (TABLE_BYTES_PER_POINT + STASH) * pts_step),
+            "density_fwd": (FLOP_FWD_PER_POINT * pts_step, TABLE_BYTES_PER_POINT * pts_step),
+            "density_fwd_loss": (FLOP_FWD_PER_POINT * pts_step, TABLE_BYTES_PER_POINT * pts_step),
+            "density_bwd": (FLOP_FWDBWD_PER_POINT * pts_step, TABLE_BYTES_PER_POINT * pts_step),
             "adam": (0, 32 * eng.n_params),
             # peer exchange: per rank 4 B/param zeroed + its 1/W slice: W gradient reads, p/m/v read+write, W parameter writes
             "adam_exchange": (0, 4 * eng.n_params + (eng.n_params // world) * (4 * world + 24 + 4 * world)),
@@ -534,15 +631,25 @@ def main():
                 flops, nbytes = algo[name]
                 k.update(tflops=flops / (mean_ms * 1e-3) / 1e12, algorithmic_gbs=nbytes / (mean_ms * 1e-3) / 1e9)
             kernels[name] = k
-        # gather / reduction operation rates against the measured L2-resident rates (scripts/microbench.py):
-        # these, not bytes, are what bound the encoder on this machine
+        # What actually bounds the encoder on this machine: the table is L2-resident, so neither kernel is near an
+        # HBM byte roofline; the gather is bound by address-divergent L1TEX wavefronts / L2 sectors, the scatter by the rate at
+        # which L2 performs float reductions.  Operation counts come from the committed ncu capture of the same kernel
+        # (lts__t_sectors_srcunit_tex_op_{read,red}: sectors that reached L2 AFTER pair merging, warp aggregation and L1 hits).
+        def limiter(name, metric, peak, label):
+            nc = ncu_summary(name)
+            if name not in kernels or not nc or metric not in nc:
+                return None
+            ops = nc[metric]
+            g = ops / (kernels[name]["ms"] * 1e-3) / 1e9
+            return {"bound": label, "ops_per_launch": ops, "ops_source": nc["file"] + ":" + metric, "achieved_gops": g, "peak_gops": peak,
+                    "frac": g / peak, "peak_source": "profiles/r1_microbench_l2_rates.json (random 8-byte accesses over an L2-resident 57 MB buffer)"}
         for fk in ("density_fwd", "density_fwd_loss"):
-            if fk in kernels:
-                kernels[fk]["gather_gops"] = 128 * pts_step / (kernels[fk]["ms"] * 1e-3) / 1e9
-                kernels[fk]["gather_gops_measured_peak"] = 263.5
-        if "density_bwd" in kernels:
-            kernels["density_bwd"]["reduction_gops"] = 128 * pts_step / (kernels["density_bwd"]["ms"] * 1e-3) / 1e9
-            kernels["density_bwd"]["reduction_gops_measured_peak"] = 184.0
+            lim = limiter(fk, "lts__t_sectors_srcunit_tex_op_read.sum", L2_GATHER_GOPS, "l1tex_gather")
+            if lim:
+                kernels[fk]["limiter"] = lim
+        lim = limiter("density_bwd", "lts__t_sectors_srcunit_tex_op_red.sum", L2_RED_GOPS, "l2_atomic")
+        if lim:
+            kernels["density_bwd"]["limiter"] = lim
         dom = max((n for n in kernels if n in algo), key=lambda n: kernels[n]["ms"])
         flops, nbytes = algo[dom]
         achieved = kernels[dom]["algorithmic_gbs"]
@@ -552,13 +659,16 @@ def main():
                     "algorithmic_bytes_per_launch": nbytes, "peak_source": peaks["source"], "kernel_ms": kernels[dom]["ms"],
                     "kernel_share_of_step": kernels[dom]["share"],
                     "tensor_tflops": kernels[dom]["tflops"], "tensor_frac": kernels[dom]["tflops"] / peaks["tensor"],
-                    "note": "algorithmic bytes = 1024 B/point of table entries reduced (gathered in forward) + 128 B/point encoding stash; the "
-                            "table (57 MB) and the stash (25 MB) are L2-resident, so DRAM traffic is below the algorithmic bytes and the "
-                            "applicable bound is the reduction / gather OPERATION rate (see kernels.*.reduction_gops vs its measured peak; "
-                            "the aggregated and pair-merged scatter issues fewer operations than the 128 per point counted here)"}
+                    "limiter": kernels[dom].get("limiter"),
+                    "note": "algorithmic bytes = 1024 B/point of table entries reduced (gathered in forward) (SURVEY.md 8d); the 57 MB table "
+                            "and the 28 MB stash are L2-resident, so DRAM traffic is far below the algorithmic bytes and `frac` against the "
+                            "HBM peak is not the distance to the applicable roofline: that is `limiter` (L2 reduction / gather operation "
+                            "rate against its measured peak)"}
         line = {
             "metric": "train samples/sec (rays x samples / s)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tables, sampling, loss, Adam: fp32; MLP products: bf16x3 split operands on tcgen05, fp32 accumulation in TMEM)",
+            "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (rays sharded, parameters replicated; exchange: " + {
                            "push": "one fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (gradients pushed to their "
                                    "owners, parameters pushed back: stores only)",
@@ -581,7 +691,11 @@ def main():
             "gpu_launches": eng.launches_per_step * K,
             "roofline": roofline,
             "kernels": kernels,
-            "final_loss": final_loss, "host_loss": host_loss, "host_loss_pipelined": piped_loss,
+            "final_loss": final_loss, "final_loss_all_ranks": loss_all, "host_loss": host_loss, "host_loss_pipelined": piped_loss,
+            # N > 1 correctness, checked after the timed region: max |param - param on rank 0| over all ranks (0.0 = bit-identical
+            # replicas) and the exchange kernel's error word (0 = no bounded spin ever gave up), max over ranks
+            "replica_divergence": replica_div, "exchange_error_word": int(err_word.item()),
+            "dp_loss_rule": "sum over ranks of the reference's chunked loss (= one GPU on the concatenated batch with the same chunk boundaries)",
         }
         if extra is not None:
             line["workloads"] = extra
@@ -589,12 +703,19 @@ def main():
             rc = reference_cuda_numbers()
             if rc:
                 line["reference_cuda"] = rc
+                for wk in ("large_batch", "voxel_query_512"):
+                    if extra is not None and wk in rc and wk in extra:
+                        extra[wk]["reference_cuda"] = rc[wk]
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=8, warmup=2)
             line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
                                     "sample": "8 timed steps of 1024 rays x 192 samples after 2 warm-up ("
                                               + ("the reference's own Python with its hash-grid kernels compiled for the host, OpenMP"
                                                  if r["kind"] == "reference" else "oracle port: C hash grid with OpenMP + torch-CPU MLP/render/Adam") + ")"}
+            if extra is not None:
+                for wk, v in cpu_extra_baselines().items():
+                    if wk in extra:
+                        extra[wk]["cpu_baseline"] = v
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

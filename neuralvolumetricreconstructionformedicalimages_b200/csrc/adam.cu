@@ -8,7 +8,7 @@
 // The arithmetic follows torch's multi-tensor (foreach) Adam op by op, each op with its own
 // rounding, so that the fused step can be compared bit for bit with torch.optim.Adam:
 //   m  = lerp(m, g, 1-b1)              -> fma(w, g - m, m)        (weight < 0.5 branch)
-//   v  = v*b2 ; v = addcmul(v, g, g, 1-b2) -> fma((1-b2)*g, g, v)
+//   v  = v*b2 ; v = addcmul(v, g, g, 1-b2) -> fma(1-b2, g*g, v)
 //   dn = sqrt(v) / sqrt(1-b2^t) + eps
 //   p  = addcdiv(p, m, dn, -lr/(1-b1^t)) -> fma(-step_size, m/dn, p)
 #include <stdlib.h>

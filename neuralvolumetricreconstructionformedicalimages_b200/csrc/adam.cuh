@@ -2,7 +2,7 @@
 // (exchange.cu).  Follows torch's multi-tensor (foreach) Adam op by op, each op with its own rounding, so that the step can
 // be compared bit for bit with torch.optim.Adam:
 //   m  = lerp(m, g, 1-b1)                    -> fma(w, g - m, m)        (weight < 0.5 branch)
-//   v  = v*b2 ; v = addcmul(v, g, g, 1-b2)   -> fma((1-b2)*g, g, v)
+//   v  = v*b2 ; v = addcmul(v, g, g, 1-b2)   -> fma(1-b2, g*g, v)        (the foreach functor: input + scalar * (t1 * t2))
 //   dn = sqrt(v) / sqrt(1-b2^t) + eps
 //   p  = addcdiv(p, m, dn, -lr/(1-b1^t))     -> fma(-step_size, m/dn, p)
 #pragma once
@@ -40,7 +40,7 @@ __device__ __forceinline__ void adam_one(float &p, const float g, float &m, floa
     const float gg = c.gscale == 1.0f ? g : __fmul_rn(g, c.gscale);
     m = __fmaf_rn(c.w1, __fsub_rn(gg, m), m);
     v = __fmul_rn(v, c.beta2);
-    v = __fmaf_rn(__fmul_rn(c.w2, gg), gg, v);
+    v = __fmaf_rn(c.w2, __fmul_rn(gg, gg), v);
     const float dn = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
     p = __fmaf_rn(c.neg_step, __fdiv_rn(m, dn), p);
 }

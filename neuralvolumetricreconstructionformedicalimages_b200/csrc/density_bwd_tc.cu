@@ -401,14 +401,9 @@ __global__ void __launch_bounds__(bound_threads(NSW), 2) k_density_bwd_ws(const 
                     part = __fmaf_rn(h2[i], small->w3[16 * half + i], part);
                 }
                 // the two halves of a row live in warps w and w + 4: each pair of warps has its own 64-thread barrier
-                auto pair_sync = [&]() {
-                    switch (warp & 3) {
-                        case 0: umma::named_bar_sync_imm<4>(64); break;
-                        case 1: umma::named_bar_sync_imm<5>(64); break;
-                        case 2: umma::named_bar_sync_imm<6>(64); break;
-                        default: umma::named_bar_sync_imm<7>(64); break;
-                    }
-                };
+                // (hardware barriers are a per-SM resource shared by the resident CTAs: this kernel uses ids 0-3 only -- with 8 of
+                // them only one CTA per SM was resident)
+                auto pair_sync = [&]() { umma::named_bar_sync_imm<2>(N_EPI); };
                 if (half == 1) xchg[r] = part;
                 pair_sync();
                 if (half == 0) {
@@ -618,7 +613,24 @@ int launch_bwd_ws_n(const GridParams &gp, const nafb_mlp &mp, const SamplerParam
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_density_bwd_ws<SRC, C, NSW>, NTW, BWS_SMEM);
         if (e != cudaSuccess || n < 1) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): the kernel does not fit on this device (%s)", cudaGetErrorString(e));
         per_sm[dev] = n > 2 ? 2 : n;
-        if (nafb_debug_flags() & 32) fprintf(stderr, "[nafb] k_density_bwd_ws<%d,%d,%d>: %d CTA(s) per SM, %u B shared memory\n", SRC, C, NSW, n, BWS_SMEM);
+        if (nafb_debug_flags() & 32) {
+            fprintf(stderr, "[nafb] k_density_bwd_ws<%d,%d,%d>: %d CTA(s) per SM, %u B shared memory\n", SRC, C, NSW, n, BWS_SMEM);
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, k_density_bwd_ws<SRC, C, NSW>);
+            fprintf(stderr, "[nafb]   regs %d static smem %zu maxDyn %d maxThreads %d carveout %d\n", fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes,
+                    fa.maxThreadsPerBlock, fa.preferredShmemCarveout);
+            for (int thr : {128, 256, 288, 384, 416, 512, 544})
+                for (unsigned sm : {0u, 49152u, 65536u, 98304u, BWS_SMEM}) {
+                    int q = -1;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_density_bwd_ws<SRC, C, NSW>, thr, sm);
+                    fprintf(stderr, "[nafb]   occupancy(threads %d, smem %u) = %d\n", thr, sm, q);
+                }
+            int v = 0;
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev); fprintf(stderr, "[nafb]   smem/SM %d", v);
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxRegistersPerMultiprocessor, dev); fprintf(stderr, " regs/SM %d", v);
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxThreadsPerMultiProcessor, dev); fprintf(stderr, " threads/SM %d", v);
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxBlocksPerMultiprocessor, dev); fprintf(stderr, " blocks/SM %d\n", v);
+        }
     }
     const int cap = nafb_sm_count() * per_sm[dev];
     if (grid > cap) grid = cap;

@@ -770,6 +770,11 @@ class NAFEngine:
             dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.pg)   # slices are disjoint
         return full
 
+    def optimizer_moments(self):
+        """(step, exp_avg, exp_avg_sq) with the moments as FLAT full-length vectors in the layout of flat_param (diagnostics and
+        tests; collective with a peer-memory exchange, like optimizer_state_dict)."""
+        return self.step_count, self._full_state(self.exp_avg), self._full_state(self.exp_avg_sq)
+
     def _param_slices(self):
         """(parameter, offset, numel) of the module's parameters inside the flat vector, in net.parameters() order."""
         params = [self.net.encoder.embeddings] + self.net.flat_params()

@@ -4,7 +4,9 @@
     pinned against torch.optim.Adam (test_gpu_parity.py::test_adam_matches_torch); gradient double buffering; flags;
   * NAFEngine(exchange="peer") on one GPU trains like the default engine;
   * two GPUs (skipped when the box has one): two ranks over NCCL + CUDA IPC; the peer path keeps the replicas
-    bit-identical and agrees with the NCCL all-reduce path.
+    bit-identical and agrees with the NCCL all-reduce path; a checkpoint rollback re-arms the epoch flags; two ranks equal ONE
+    GPU working on the concatenated batch (the data-parallel loss rule); an injected peer_open failure on one rank makes
+    every rank fall back to NCCL together.
 """
 import ctypes
 import os
@@ -99,9 +101,12 @@ def test_engine_peer_mode_single_gpu_matches_default():
         torch.cuda.synchronize()
         if eng.px is not None:
             assert eng.px.error_word() == 0
-        sd = eng.optimizer_state_dict()
-        assert sd["exp_avg"].numel() == eng.n_params and sd["step"] == 4
-        params.append((eng.flat_param.clone(), sd["exp_avg_sq"], float(loss.item())))
+        step, m_flat, v_flat = eng.optimizer_moments()
+        assert m_flat.numel() == eng.n_params and step == 4
+        sd = eng.optimizer_state_dict()                      # torch.optim.Adam layout (what the reference's ckpt.tar holds)
+        assert float(sd["state"][0]["step"]) == 4.0 and sd["state"][0]["exp_avg_sq"].shape == (7131219, 2)
+        eng.check_health()
+        params.append((eng.flat_param.clone(), v_flat, float(loss.item())))
     pb, vb, lb = params[-1]
     for pa, va, la in params[:-1]:
         assert abs(la - lb) <= 1e-5 * abs(lb)
@@ -134,15 +139,48 @@ def _worker(rank, world, port, out_dir):
         except RuntimeError:
             pass
         for mode in modes:
-            eng = NAFEngine(_net(dev, seed=rank), lr=1e-3, n_samples=S, perturb=True, loss_chunk=100, use_cuda_graph=True, exchange=mode)
+            eng = NAFEngine(_net(dev, seed=rank), lr=1e-3, n_samples=S, perturb=True, loss_chunk=128, use_cuda_graph=True, exchange=mode)
             assert eng.exchange_mode == mode, eng.exchange_mode
             for rays, projs, t_rand in batches:
                 eng.train_step(rays.to(dev), projs.to(dev), None, t_rand.to(dev))
             torch.cuda.synchronize()
             div = parallel.replica_divergence(eng.flat_param)
             err = eng.px.error_word() if eng.px is not None else 0
+            eng.check_health()
+            _, _, v_flat = eng.optimizer_moments()
+            res[mode] = dict(param=eng.flat_param.cpu(), v=v_flat.cpu(), div=div, err=err)
+            # a rollback (checkpoint restore to an EARLIER step) must re-arm the epoch flags: two more steps stay in lock-step
             sd = eng.optimizer_state_dict()
-            res[mode] = dict(param=eng.flat_param.cpu(), v=sd["exp_avg_sq"].cpu(), div=div, err=err)
+            for _ in range(2):
+                rays, projs, t_rand = batches[0]
+                eng.train_step(rays.to(dev), projs.to(dev), None, t_rand.to(dev))
+            eng.load_optimizer_state_dict(sd)
+            for rays, projs, t_rand in batches[:2]:
+                eng.train_step(rays.to(dev), projs.to(dev), None, t_rand.to(dev))
+            torch.cuda.synchronize()
+            res[mode]["div_after_rollback"] = parallel.replica_divergence(eng.flat_param)
+            res[mode]["err_after_rollback"] = eng.px.error_word() if eng.px is not None else 0
+            del eng
+        # ---- the data-parallel rule: W ranks == ONE GPU on the concatenated batch with the same chunk boundaries (the loss is the
+        # reference's sum of chunk means, train.py:69-127; the rank-summed gradient goes to Adam unscaled)
+        solo_group = [dist.new_group([r]) for r in range(world)][rank]
+        solo = NAFEngine(_net(dev, seed=0), lr=1e-3, n_samples=S, perturb=True, loss_chunk=128, use_cuda_graph=False, process_group=solo_group)
+        assert solo.world_size == 1
+        all_batches = [_batches(r, 5)[0] for r in range(world)]
+        for k in range(5):
+            cat = [torch.cat([all_batches[r][k][j] for r in range(world)], 0).to(dev) for j in range(3)]
+            solo.train_step(cat[0], cat[1], None, cat[2])
+        torch.cuda.synchronize()
+        res["solo"] = dict(param=solo.flat_param.cpu())
+        # ---- a peer_open failure on ONE rank: every rank must leave the set-up together and agree on the NCCL fallback
+        os.environ["NAFB_TEST_FAIL_PEER_OPEN"] = "1"
+        eng = NAFEngine(_net(dev, seed=rank), lr=1e-3, n_samples=S, perturb=True, loss_chunk=128, exchange="auto")
+        del os.environ["NAFB_TEST_FAIL_PEER_OPEN"]
+        assert eng.exchange_mode == "nccl", eng.exchange_mode
+        rays, projs, t_rand = batches[0]
+        eng.train_step(rays.to(dev), projs.to(dev), None, t_rand.to(dev))
+        torch.cuda.synchronize()
+        res["fallback_div"] = parallel.replica_divergence(eng.flat_param)
         if rank == 0:
             torch.save(res, os.path.join(out_dir, "res.pt"))
         dist.barrier()
@@ -155,10 +193,16 @@ def test_two_gpu_peer_exchange_matches_nccl(tmp_path):
     import torch.multiprocessing as mp
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    res = torch.load(os.path.join(str(tmp_path), "res.pt"))
+    res = torch.load(os.path.join(str(tmp_path), "res.pt"), weights_only=False)
     print("exchange modes exercised:", sorted(res))
-    for mode in res:
+    modes = [m for m in res if isinstance(res[m], dict) and "div" in res[m]]
+    for mode in modes:
         assert res[mode]["err"] == 0 and res[mode]["div"] == 0.0, mode    # no timed-out flag, replicas bit-identical
+        assert res[mode]["err_after_rollback"] == 0 and res[mode]["div_after_rollback"] == 0.0, mode
         if mode != "nccl":
             np.testing.assert_allclose(res[mode]["param"].numpy(), res["nccl"]["param"].numpy(), rtol=0, atol=5e-5)
             np.testing.assert_allclose(res[mode]["v"].numpy(), res["nccl"]["v"].numpy(), rtol=2e-3, atol=1e-12)
+    assert res["fallback_div"] == 0.0
+    # two ranks == one GPU on the concatenated batch (replicas start from rank 0's parameters in both runs)
+    a, b = res["nccl"]["param"].numpy(), res["solo"]["param"].numpy()
+    assert (np.abs(a - b) > 5e-5).mean() < 1e-4 and np.abs(a - b).max() < 2.1e-3 * 5   # 5 steps of lr 1e-3; float-atomic order differs

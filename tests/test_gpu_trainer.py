@@ -47,7 +47,7 @@ def _alias_src():
 
 def _phantom_pickle(path, n_train=6, n_val=2):
     from neuralvolumetricreconstructionformedicalimages_b200.dataset import phantom as PH
-    geometry = dict(DSD=1500.0, DSO=1000.0, nDetector=[64, 64], dDetector=[4.0, 4.0], nVoxel=[32, 32, 32], dVoxel=[4.0, 4.0, 4.0],
+    geometry = dict(DSD=1500.0, DSO=1000.0, nDetector=[128, 128], dDetector=[2.0, 2.0], nVoxel=[32, 32, 32], dVoxel=[4.0, 4.0, 4.0],
                     offOrigin=[0, 0, 0], offDetector=[0, 0], accuracy=0.5, mode="cone", filter=None)
     PH.save_pickle(PH.make_dataset_dict(geometry, n_train, n_val), path)
 
