@@ -36,13 +36,13 @@ using namespace tc;
 
 namespace {
 
-// Registers are allocated per group of 4 warps, and two CTAs must share the SM's 64 K registers (the chain of one CTA hides
-// the latencies of the other): NSW = 4 scatter warps -> 13 warps (16 allocated) x 64 registers; NSW = 8 -> 17 warps (20
-// allocated) x 48 registers.  The launch bound below is what makes ptxas stay inside that budget.
+// Two CTAs must share the SM's 64 K registers (the chain of one CTA hides the latencies of the other): NSW = 4 scatter warps
+// -> 13 warps x 64 registers; NSW = 8 -> 17 warps x 56 registers.  The launch bound below is what makes ptxas stay inside
+// that budget.
 constexpr int N_EPI = 256;
 constexpr int WARP_ISSUE = 8, WARP_SCATTER0 = 9;
 __host__ __device__ constexpr int block_threads(int nsw) { return 32 * (9 + nsw); }
-__host__ __device__ constexpr int bound_threads(int nsw) { return nsw == 4 ? 512 : 640; }
+__host__ __device__ constexpr int bound_threads(int nsw) { return nsw == 4 ? 512 : 544; }
 constexpr uint32_t BAR_THREADS = N_EPI + 32;   // 256 arrive + the issue warp syncs
 
 // ---- shared memory
@@ -126,6 +126,18 @@ __global__ void __launch_bounds__(bound_threads(NSW), 2) k_density_bwd_ws(const 
     constexpr int NTW = block_threads(NSW);
     constexpr uint32_t N_SCATTER_WARPS = NSW;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    // debug (dbg & 32): thread 0 of CTA 0 records clock64 / %globaltimer at the kernel's milestones in slot 3, entries 112..
+    long long *kst = (dbg & 32) && t == 0 && blockIdx.x == 0 ? dbg_stamps + 3 * 128 + 96 : nullptr;
+    auto kstamp = [&](int i) {
+        if (kst) {
+            unsigned long long g, c;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)::"memory");
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)::"memory");   // (memory clobber: not to be scheduled across a barrier)
+            kst[2 * i] = (long long)c;
+            kst[2 * i + 1] = (long long)g;
+        }
+    };
+    kstamp(0);
     load_weight_images(mp, W_hi, W_lo, small);
     if (t < NAFB_MAX_LEVELS) lvs[t] = gp.lv[t];
     // operand buffers start finite: the stacked 128-feature window of the dW products reads rows that are never written
@@ -147,6 +159,7 @@ __global__ void __launch_bounds__(bound_threads(NSW), 2) k_density_bwd_ws(const 
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = ctl->tmem_base;
+    kstamp(1);   // set-up done
     const uint64_t n_tiles = (P + TILE - 1) / TILE;
     const bool did_work = blockIdx.x < n_tiles;
     const bool do_scatter = grad_table != nullptr && !(dbg & 1);
@@ -473,34 +486,25 @@ __global__ void __launch_bounds__(bound_threads(NSW), 2) k_density_bwd_ws(const 
         umma::fence_before_sync();
     }
 
-    // ================= flush the MLP gradients of this CTA into its slot of the partials workspace
-    float *mine = partials + (size_t)blockIdx.x * PTOTAL;
-    __syncthreads();
-    umma::fence_after_sync();
-    // combine the per-warp column sums of the 4 warps of each half
-    if (t < 32) {   // column j of the 32-wide vectors: half = j / 16 -> warps 4*half .. 4*half+3
-        const int hj = t >> 4, cj = t & 15;
-        float s2 = 0.f, s1 = 0.f, s0 = 0.f, sw = 0.f;
-        for (int w = 0; w < 4; ++w) {
-            const float *q = wred + (4 * hj + w) * 80;
-            s2 += q[0 * 16 + cj]; s1 += q[1 * 16 + cj]; s0 += q[2 * 16 + cj]; sw += q[3 * 16 + cj];
-        }
-        mine[PB2 + t] = s2; mine[PB1 + t] = s1; mine[PB0 + t] = s0; mine[PW3 + t] = sw;
-        if (t == 0) {
-            float s3 = 0.f;
-            for (int w = 0; w < 4; ++w) s3 += wred[w * 80 + 64];
-            mine[PB3] = s3;
-            mine[PB3 + 1] = mine[PB3 + 2] = mine[PB3 + 3] = 0.f;
-        }
-    }
-    // tensor-core side: dW_l[o][k] = TMEM lane o (the G_hi rows) + TMEM lane 32 + o (the G_lo rows).  Warps 0 / 4 read the first
-    // block and warps 1 / 5 (lane quadrant 1) the second, 16 columns at a time; the second pass adds to what the first stored.
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        if ((warp & 3) == pass && warp < 8) {
-            const int half = warp >> 2;
+    // ================= the MLP gradients of this CTA -> its slot of the partials workspace -> grid-wide reduction.
+    // Only the epilogue and issue warps (288 threads, named barrier 1) take part: the scatter warps are still busy with the LAST
+    // tile's d(encoding) -- a tail with nothing to overlap, were it not for this work -- and join at the final __syncthreads.
+    constexpr int NTF = N_EPI + 32;   // threads of the tail
+    if (warp <= WARP_ISSUE) {
+        float *mine = partials + (size_t)blockIdx.x * PTOTAL;
+        kstamp(2);   // epilogue warp 0 has left its tile loop
+        umma::named_bar_sync_imm<1>(NTF);
+        umma::fence_after_sync();
+        // Weight gradients: dW_l[o][k] = TMEM lane o (the G_hi rows) + TMEM lane 32 + o (the G_lo rows).  Warps 0 / 4 read the
+        // first block, warps 1 / 5 (lane quadrant 1) the second, 16 columns at a time, into two images in shared memory (the
+        // operand buffers are dead: every MMA has completed); rows padded by one float against bank conflicts.
+        float *stg = reinterpret_cast<float *>(smem);                   // [2][SW_TOTAL]
+        constexpr int SW0 = 0, SW1 = 32 * 33, SW2 = 2 * 32 * 33, SW_TOTAL = 2 * 32 * 33 + 32 * 65;
+        static_assert(2 * SW_TOTAL * sizeof(float) <= 2 * ENC_BYTES + AH_BYTES, "staging area of the weight-gradient dump");
+        if ((warp & 3) < 2 && warp < 8) {
+            const int pass = warp & 3, half = warp >> 2;
             float w16[16];
-            auto dump = [&](uint32_t tcol, int dst, int ldw, int ncols) {
+            auto dump = [&](uint32_t tcol, int dst, int ld, int ncols) {
                 for (int c0 = 16 * half; c0 < ncols; c0 += 32) {
                     if (did_work) {
                         umma::tmem_ld16(tmem + ((uint32_t)(pass * 32) << 16) + tcol + c0, w16);
@@ -510,93 +514,122 @@ __global__ void __launch_bounds__(bound_threads(NSW), 2) k_density_bwd_ws(const 
                         for (int i = 0; i < 16; ++i) w16[i] = 0.f;
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float *q = mine + dst + lane * ldw + c0 + i;
-                        *q = pass ? *q + w16[i] : w16[i];
-                    }
+                    for (int i = 0; i < 16; ++i) stg[pass * SW_TOTAL + dst + lane * ld + c0 + i] = w16[i];
                 }
             };
-            dump(T_DW0, PW0, 32, 32);
-            dump(T_DW1, PW1, 32, 32);
-            dump(T_DW2, PW2, 64, 64);
+            dump(T_DW0, SW0, 33, 32);
+            dump(T_DW1, SW1, 33, 32);
+            dump(T_DW2, SW2, 65, 64);
         }
         umma::fence_before_sync();
-        __syncthreads();
-    }
-    if (warp == 0) umma::tmem_dealloc(tmem, T_COLS);
-
-    // ================= gW / gb += sum over the CTAs' rows.  One grid-wide barrier replaces a separate reduction kernel: the grid
-    // is sized from the occupancy of this kernel on this device (nafb_ws_bwd_grid: every CTA is resident), so every CTA can wait
-    // for all rows and then sum its share of the columns -- units of 16 columns x 34 row slices; a slice adds its rows in order
-    // with four loads in flight, the slice sums are added in order: the summation tree is a function of the grid size only.
-    // sync[0] counts arrivals, sync[1] departures; the last CTA to leave clears both (the workspace starts zero-filled).
-    // A CTA that has waited GRID_BARRIER_TIMEOUT_NS raises sync[2] (the host reads it: NAFEngine.check_health) and leaves.
-    if (sync == nullptr) return;
-    __shared__ uint32_t s_ok;
-    if (t == 0) {
-        __threadfence();
-        atomicAdd(sync, 1u);
-        uint32_t seen;
-        unsigned long long t0 = 0;
-        s_ok = 1u;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync) : "memory");
-            if (seen >= gridDim.x) break;
-            __nanosleep(64);
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            if (now - t0 > 30000000000ull) {   // 30 s: a CTA of this grid never became resident
-                atomicExch(sync + 2, 1u);
-                s_ok = 0u;
-                break;
+        umma::named_bar_sync_imm<1>(NTF);
+        // coalesced copy-out: hi block + lo block
+        for (int i = t; i < PW3; i += NTF) {
+            int si;
+            if (i < PW1) si = SW0 + (i >> 5) * 33 + (i & 31);
+            else if (i < PW2) si = SW1 + ((i - PW1) >> 5) * 33 + ((i - PW1) & 31);
+            else si = SW2 + ((i - PW2) >> 6) * 65 + ((i - PW2) & 63);
+            mine[i] = stg[si] + stg[SW_TOTAL + si];
+        }
+        // SIMT-side column sums of the 4 warps of each half
+        if (t < 32) {   // column j of the 32-wide vectors: half = j / 16 -> warps 4*half .. 4*half+3
+            const int hj = t >> 4, cj = t & 15;
+            float s2 = 0.f, s1 = 0.f, s0 = 0.f, sw = 0.f;
+            for (int w = 0; w < 4; ++w) {
+                const float *q = wred + (4 * hj + w) * 80;
+                s2 += q[0 * 16 + cj]; s1 += q[1 * 16 + cj]; s0 += q[2 * 16 + cj]; sw += q[3 * 16 + cj];
+            }
+            mine[PB2 + t] = s2; mine[PB1 + t] = s1; mine[PB0 + t] = s0; mine[PW3 + t] = sw;
+            if (t == 0) {
+                float s3 = 0.f;
+                for (int w = 0; w < 4; ++w) s3 += wred[w * 80 + 64];
+                mine[PB3] = s3;
+                mine[PB3 + 1] = mine[PB3 + 2] = mine[PB3 + 3] = 0.f;
             }
         }
-    }
-    __syncthreads();
-    if (s_ok) {
-        const int rows = (int)gridDim.x, j = t & 15, k = t >> 4;   // NTW = 544 -> k in 0..33
-        constexpr int SL = NTW / 16;
-        static_assert(SL * 16 <= (int)WRED_FLOATS, "wred too small for the final reduction");
-        for (int u = blockIdx.x; u * 16 < PTOTAL; u += rows) {
-            const int col = u * 16 + j;
-            float s = 0.f;
-            if (col < PTOTAL) {
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                int bb = k;
-                for (; bb + 3 * SL < rows; bb += 4 * SL) {
-                    s0 += __ldcg(partials + (size_t)bb * PTOTAL + col);
-                    s1 += __ldcg(partials + (size_t)(bb + SL) * PTOTAL + col);
-                    s2 += __ldcg(partials + (size_t)(bb + 2 * SL) * PTOTAL + col);
-                    s3 += __ldcg(partials + (size_t)(bb + 3 * SL) * PTOTAL + col);
+        kstamp(4);   // partials written
+        // ---- gW / gb += sum over the CTAs' rows.  One grid-wide barrier replaces a separate reduction kernel: the grid is sized
+        // so that every CTA is resident (launch_bwd_ws_n), so every CTA can wait for all rows and then sum its share of the
+        // columns -- units of 16 columns x 18 row slices; a slice adds its rows in order with four loads in flight, the slice
+        // sums are added in order: the summation tree is a function of the grid size only (deterministic).
+        // sync[0] counts arrivals, sync[1] departures; the last CTA to leave clears both (the workspace starts zero-filled).
+        // A CTA that has waited 30 s raises sync[2] (the host reads it: NAFEngine.check_health) and leaves without reducing.
+        if (sync != nullptr) {
+            __shared__ uint32_t s_ok;
+            __threadfence();
+            umma::named_bar_sync_imm<1>(NTF);
+            if (t == 0) {
+                atomicAdd(sync, 1u);
+                uint32_t seen;
+                unsigned long long t0 = 0;
+                s_ok = 1u;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync) : "memory");
+                    if (seen >= gridDim.x) break;
+                    __nanosleep(64);
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > 30000000000ull) {   // a CTA of this grid never became resident
+                        atomicExch(sync + 2, 1u);
+                        s_ok = 0u;
+                        break;
+                    }
                 }
-                float t0 = 0.f, t1 = 0.f, t2 = 0.f;   // at most three left
-                if (bb < rows) t0 = __ldcg(partials + (size_t)bb * PTOTAL + col);
-                if (bb + SL < rows) t1 = __ldcg(partials + (size_t)(bb + SL) * PTOTAL + col);
-                if (bb + 2 * SL < rows) t2 = __ldcg(partials + (size_t)(bb + 2 * SL) * PTOTAL + col);
-                s = ((s0 + s1) + (s2 + s3)) + ((t0 + t1) + t2);
             }
-            wred[k * 16 + j] = s;
-            __syncthreads();
-            if (t < 16 && col < PTOTAL) {
-                float tot = 0.f;
+            umma::named_bar_sync_imm<1>(NTF);
+            kstamp(5);   // grid barrier passed
+            if (s_ok) {
+                const int rows = (int)gridDim.x, j = t & 15, k = t >> 4;   // NTF = 288 -> k in 0..17
+                constexpr int SL = NTF / 16;
+                static_assert(SL * 16 <= (int)WRED_FLOATS, "wred too small for the final reduction");
+                for (int u = blockIdx.x; u * 16 < PTOTAL; u += rows) {
+                    const int col = u * 16 + j;
+                    float s = 0.f;
+                    if (col < PTOTAL) {
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                        int bb = k;
+                        for (; bb + 3 * SL < rows; bb += 4 * SL) {
+                            s0 += __ldcg(partials + (size_t)bb * PTOTAL + col);
+                            s1 += __ldcg(partials + (size_t)(bb + SL) * PTOTAL + col);
+                            s2 += __ldcg(partials + (size_t)(bb + 2 * SL) * PTOTAL + col);
+                            s3 += __ldcg(partials + (size_t)(bb + 3 * SL) * PTOTAL + col);
+                        }
+                        float t0 = 0.f, t1 = 0.f, t2 = 0.f;   // at most three left
+                        if (bb < rows) t0 = __ldcg(partials + (size_t)bb * PTOTAL + col);
+                        if (bb + SL < rows) t1 = __ldcg(partials + (size_t)(bb + SL) * PTOTAL + col);
+                        if (bb + 2 * SL < rows) t2 = __ldcg(partials + (size_t)(bb + 2 * SL) * PTOTAL + col);
+                        s = ((s0 + s1) + (s2 + s3)) + ((t0 + t1) + t2);
+                    }
+                    wred[k * 16 + j] = s;
+                    umma::named_bar_sync_imm<1>(NTF);
+                    if (t < 16 && col < PTOTAL) {
+                        float tot = 0.f;
 #pragma unroll
-                for (int q = 0; q < SL; ++q) tot += wred[q * 16 + t];
-                float *dst = nullptr;
-                if (col < PW1) dst = gr.gW[0] ? gr.gW[0] + col : nullptr;
-                else if (col < PW2) dst = gr.gW[1] ? gr.gW[1] + (col - PW1) : nullptr;
-                else if (col < PW3) dst = gr.gW[2] ? gr.gW[2] + (col - PW2) : nullptr;
-                else if (col < PB0) dst = gr.gW[3] ? gr.gW[3] + (col - PW3) : nullptr;
-                else if (col < PB1) dst = gr.gb[0] ? gr.gb[0] + (col - PB0) : nullptr;
-                else if (col < PB2) dst = gr.gb[1] ? gr.gb[1] + (col - PB1) : nullptr;
-                else if (col < PB3) dst = gr.gb[2] ? gr.gb[2] + (col - PB2) : nullptr;
-                else if (col == PB3) dst = gr.gb[3];
-                if (dst) *dst += tot;
+                        for (int q = 0; q < SL; ++q) tot += wred[q * 16 + t];
+                        float *dst = nullptr;
+                        if (col < PW1) dst = gr.gW[0] ? gr.gW[0] + col : nullptr;
+                        else if (col < PW2) dst = gr.gW[1] ? gr.gW[1] + (col - PW1) : nullptr;
+                        else if (col < PW3) dst = gr.gW[2] ? gr.gW[2] + (col - PW2) : nullptr;
+                        else if (col < PB0) dst = gr.gW[3] ? gr.gW[3] + (col - PW3) : nullptr;
+                        else if (col < PB1) dst = gr.gb[0] ? gr.gb[0] + (col - PB0) : nullptr;
+                        else if (col < PB2) dst = gr.gb[1] ? gr.gb[1] + (col - PB1) : nullptr;
+                        else if (col < PB3) dst = gr.gb[2] ? gr.gb[2] + (col - PB2) : nullptr;
+                        else if (col == PB3) dst = gr.gb[3];
+                        if (dst) *dst += tot;
+                    }
+                    umma::named_bar_sync_imm<1>(NTF);
+                }
             }
-            __syncthreads();
+            kstamp(6);   // reduction done
+            if (t == 0 && atomicAdd(sync + 1, 1u) == gridDim.x - 1) { sync[0] = 0u; sync[1] = 0u; }
         }
     }
-    if (t == 0 && atomicAdd(sync + 1, 1u) == gridDim.x - 1) { sync[0] = 0u; sync[1] = 0u; }
+    // every role is done with tensor memory (the scatter warps have read the last d(encoding))
+    umma::fence_before_sync();
+    __syncthreads();
+    kstamp(3);
+    if (warp == 0) umma::tmem_dealloc(tmem, T_COLS);
 }
 
 template <int SRC, int C, int NSW>
@@ -605,32 +638,29 @@ int launch_bwd_ws_n(const GridParams &gp, const nafb_mlp &mp, const SamplerParam
     constexpr int NTW = block_threads(NSW);
     static bool configured[NAFB_MAX_DEVICES] = {};
     NAFB_CONFIGURE_SMEM(configured, (k_density_bwd_ws<SRC, C, NSW>), (int)BWS_SMEM, "density_backward(tc)");
-    // the grid barrier needs every CTA resident: never launch more CTAs than this kernel's occupancy on this device allows
+    // The grid barrier needs every CTA resident.  cudaOccupancyMaxActiveBlocksPerMultiprocessor (and with it cooperative launch)
+    // answers 1 for ANY kernel that allocates tensor memory, whatever its size (scripts/probe/occ_probe.cu, measured on this
+    // pool's B200), although the hardware co-schedules such CTAs; so the residency is computed here from the kernel's own
+    // resources: two CTAs per SM when shared memory, registers (allocated per warp) and the 512 TMEM columns allow it.
     static int per_sm[NAFB_MAX_DEVICES] = {};
     const int dev = nafb_current_device();
     if (per_sm[dev] == 0) {
-        int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_density_bwd_ws<SRC, C, NSW>, NTW, BWS_SMEM);
-        if (e != cudaSuccess || n < 1) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): the kernel does not fit on this device (%s)", cudaGetErrorString(e));
-        per_sm[dev] = n > 2 ? 2 : n;
-        if (nafb_debug_flags() & 32) {
-            fprintf(stderr, "[nafb] k_density_bwd_ws<%d,%d,%d>: %d CTA(s) per SM, %u B shared memory\n", SRC, C, NSW, n, BWS_SMEM);
-            cudaFuncAttributes fa;
-            cudaFuncGetAttributes(&fa, k_density_bwd_ws<SRC, C, NSW>);
-            fprintf(stderr, "[nafb]   regs %d static smem %zu maxDyn %d maxThreads %d carveout %d\n", fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes,
-                    fa.maxThreadsPerBlock, fa.preferredShmemCarveout);
-            for (int thr : {128, 256, 288, 384, 416, 512, 544})
-                for (unsigned sm : {0u, 49152u, 65536u, 98304u, BWS_SMEM}) {
-                    int q = -1;
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_density_bwd_ws<SRC, C, NSW>, thr, sm);
-                    fprintf(stderr, "[nafb]   occupancy(threads %d, smem %u) = %d\n", thr, sm, q);
-                }
-            int v = 0;
-            cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev); fprintf(stderr, "[nafb]   smem/SM %d", v);
-            cudaDeviceGetAttribute(&v, cudaDevAttrMaxRegistersPerMultiprocessor, dev); fprintf(stderr, " regs/SM %d", v);
-            cudaDeviceGetAttribute(&v, cudaDevAttrMaxThreadsPerMultiProcessor, dev); fprintf(stderr, " threads/SM %d", v);
-            cudaDeviceGetAttribute(&v, cudaDevAttrMaxBlocksPerMultiprocessor, dev); fprintf(stderr, " blocks/SM %d\n", v);
-        }
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, k_density_bwd_ws<SRC, C, NSW>);
+        if (e != cudaSuccess) NAFB_FAIL(NAFB_ERR_CUDA, "density_backward(tc): %s", cudaGetErrorString(e));
+        int smem_sm = 0, regs_sm = 0, real_dev = 0;
+        cudaGetDevice(&real_dev);
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, real_dev);
+        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, real_dev);
+        const int by_smem = smem_sm / (int)(BWS_SMEM + fa.sharedSizeBytes + 1024);
+        const int by_regs = regs_sm / (((fa.numRegs * 32 + 255) / 256 * 256) * (NTW / 32));
+        int n = by_smem < by_regs ? by_smem : by_regs;
+        if (n > (int)(512 / T_COLS)) n = 512 / T_COLS;
+        if (n < 1) NAFB_FAIL(NAFB_ERR_UNSUPPORTED, "density_backward(tc): the kernel does not fit on this device (%d B shared memory, %d registers per SM)", smem_sm, regs_sm);
+        per_sm[dev] = n;
+        if (nafb_debug_flags() & 32)
+            fprintf(stderr, "[nafb] k_density_bwd_ws<%d,%d,%d>: %d CTA(s) per SM (shared memory %d, registers %d: %d regs x %d threads), %u B shared memory\n", SRC, C,
+                    NSW, n, by_smem, by_regs, fa.numRegs, NTW, BWS_SMEM);
     }
     const int cap = nafb_sm_count() * per_sm[dev];
     if (grid > cap) grid = cap;

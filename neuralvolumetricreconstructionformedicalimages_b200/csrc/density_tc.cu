@@ -67,8 +67,16 @@ __global__ void __launch_bounds__(NT, FWD_CTAS) k_density_fwd_tc(const GridParam
         bool valid = p < P;
         float x[3] = {0.f, 0.f, 0.f};
         if constexpr (SRC == NAFB_SRC_VOXELS) valid = voxel_block_point(sp, tile, (uint32_t)r, x, p);   // 4 x 4 x 8 blocks of the lattice
+        float z_mine = 0.f, delta_mine = 0.f;   // RAYS source: this sample's depth and its ray-integral weight delta_i |d|
+        uint32_t ray_mine = 0xffffffffu;
         if (valid) {
-            if constexpr (SRC != NAFB_SRC_VOXELS) fetch_point<SRC>(sp, p, x);
+            if constexpr (SRC == NAFB_SRC_RAYS) {
+                ray_mine = P <= 0xffffffffull ? (uint32_t)p / sp.n_samples : (uint32_t)(p / sp.n_samples);
+                ray_sample_and_delta(sp, ray_mine, (uint32_t)(p - (uint64_t)ray_mine * sp.n_samples), half == 0 && (acc_out || z_out || stash), x,
+                                     z_mine, delta_mine);
+            } else if constexpr (SRC != NAFB_SRC_VOXELS) {
+                fetch_point<SRC>(sp, p, x);
+            }
             if (!(x[0] >= -sp.bound && x[0] <= sp.bound && x[1] >= -sp.bound && x[1] <= sp.bound && x[2] >= -sp.bound && x[2] <= sp.bound))
                 bad |= 1;
             if (SRC == NAFB_SRC_RAYS && pts_out && half == 0) {
@@ -161,17 +169,11 @@ __global__ void __launch_bounds__(NT, FWD_CTAS) k_density_fwd_tc(const GridParam
             if constexpr (SRC == NAFB_SRC_RAYS) {
                 if (acc_out || z_out || stash) {
                     float contrib = 0.f;
-                    uint32_t ray = 0xffffffffu;
+                    const uint32_t ray = ray_mine;
                     if (valid) {
-                        ray = (uint32_t)(p / sp.n_samples);
-                        const uint32_t i = (uint32_t)(p - (uint64_t)ray * sp.n_samples);
-                        const RayRegs R = load_ray(sp, ray);
-                        const float delta = ray_delta(sp, R, ray, i);
-                        if (stash) reinterpret_cast<float *>(stash + tile * ST_TILE + ST_TAIL_DELTA)[r] = delta;
-                        contrib = __fmul_rn(y, delta);  // render.py:201
-                        if (z_out)
-                            z_out[p] = z_sample(R.near, R.far, i, sp.n_samples, sp.lin_step, sp.perturb != 0,
-                                                jitter_for(sp, ray));
+                        if (stash) reinterpret_cast<float *>(stash + tile * ST_TILE + ST_TAIL_DELTA)[r] = delta_mine;
+                        contrib = __fmul_rn(y, delta_mine);  // render.py:201
+                        if (z_out) z_out[p] = z_mine;
                     }
                     if (acc_out) {  // warp-shuffle segmented reduction keyed by the ray id
 #pragma unroll

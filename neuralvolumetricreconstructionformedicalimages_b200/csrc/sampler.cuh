@@ -214,6 +214,42 @@ __device__ __forceinline__ float ray_delta(const SamplerParams &sp, const RayReg
     return __fmul_rn(dist, R.norm);
 }
 
+// Sample i of ray r AND its ray-integral weight delta_i |d| in one go (what fetch_point + ray_delta evaluate separately): the
+// uniform positions i-1 .. i+2 once, two jitter draws, one ray.  Same operations, same roundings: bit-identical results.
+__device__ __forceinline__ void ray_sample_and_delta(const SamplerParams &sp, uint32_t r, uint32_t i, bool want_delta, float (&x)[3], float &z0,
+                                                     float &delta) {
+    const RayRegs R = load_ray(sp, r);
+    const uint32_t S = sp.n_samples;
+    const bool perturb = sp.perturb != 0;
+    const Jitter jit = jitter_for(sp, r);
+    const float u_i = z_uniform(R.near, R.far, i, S, sp.lin_step);
+    const float u_n = i + 1 < S ? z_uniform(R.near, R.far, i + 1, S, sp.lin_step) : u_i;
+    z0 = u_i;
+    if (perturb) {
+        float lower = u_i, upper = u_i;
+        if (i > 0) lower = __fmul_rn(0.5f, __fadd_rn(u_i, z_uniform(R.near, R.far, i - 1, S, sp.lin_step)));
+        if (i + 1 < S) upper = __fmul_rn(0.5f, __fadd_rn(u_n, u_i));
+        z0 = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), jitter_uniform(jit, i)));
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = ray_point(R.o[d], R.d[d], z0, sp.clamp);
+    delta = 0.f;
+    if (want_delta) {
+        float dist = 1e-10f;
+        if (i + 1 < S) {
+            float z1 = u_n;
+            if (perturb) {
+                const float lower = __fmul_rn(0.5f, __fadd_rn(u_n, u_i));
+                float upper = u_n;
+                if (i + 2 < S) upper = __fmul_rn(0.5f, __fadd_rn(z_uniform(R.near, R.far, i + 2, S, sp.lin_step), u_n));
+                z1 = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), jitter_uniform(jit, i + 1)));
+            }
+            dist = __fsub_rn(z1, z0);
+        }
+        delta = __fmul_rn(dist, R.norm);
+    }
+}
+
 // normalisation of HashEncoder.forward (hashgrid.py:125) as ATen's CUDA kernels evaluate it:
 // (x + size) is one add; "/ (2*size)" with a python-scalar divisor is a multiply by fl(1/fl(2*size)).
 __device__ __forceinline__ float normalise01(float x, float bound, float inv_2bound) {

@@ -8,10 +8,22 @@ dev = torch.device("cuda", 0)
 eng = bench.build_engine(dev)
 _, rays_b, projs_b, mask_b, _ = bench.synthetic_batches(4, dev, 1)
 eng.use_cuda_graph = False
-for i in range(3):
-    eng.train_step(rays_b[i], projs_b[i], mask_b[i])
+from neuralvolumetricreconstructionformedicalimages_b200.engine import EventTimer
+for i in range(30):          # let the clocks ramp up: the stamps describe the LAST launch
+    eng.train_step(rays_b[i % 4], projs_b[i % 4], mask_b[i % 4])
+tm = EventTimer()
+eng.profiled_step(rays_b[0], projs_b[0], mask_b[0], None, tm)
 torch.cuda.synchronize()
-st = eng._bwd_ws[-4160:-64].view(torch.int64).cpu().numpy().reshape(4, 128)
+print("last step, CUDA events (us):", {k: round(v[0] * 1e3, 1) for k, v in tm.summary().items()})
+st = eng._bwd_ws[-4160:-64].view(torch.int64).cpu().numpy().reshape(4, 128).copy()
+ks = st[3, 96:122].reshape(13, 2)
+if ks[0, 0] > 0:
+    names_k = ["start", "set-up done", "epilogue loop done", "all roles done (scatter included), TMEM released", "partials written", "grid barrier passed", "reduction done", "dump pass 0", "dump pass 1", "TMEM released", "column sums written", "first dW block dumped", "warp 0 dumped"]
+    print("kernel milestones of CTA 0 (cycles / ns since start; MHz = cycles / us):")
+    for i in (1, 2, 4, 5, 6, 3):
+        dc, dn = ks[i, 0] - ks[0, 0], ks[i, 1] - ks[0, 1]
+        print(f"  {names_k[i]:22s} {dc:8d} cyc {dn:8d} ns   {dc / max(dn, 1) * 1e3:7.0f} MHz")
+st[3, 96:] = 0
 names = ["dsig", "wM0", "epi0", "wM1", "epi1", "wM2", "head", "stG", "wM3", "epi3", "wM4", "epi4", "next"]
 for c in range(2):
     s = st[c]
