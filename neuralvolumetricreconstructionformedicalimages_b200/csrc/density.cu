@@ -27,9 +27,7 @@ int nafb_tc_bwd_grid(uint64_t n_tiles);
 uint64_t nafb_tc_stash_bytes(uint64_t n_points);
 int nafb_launch_fwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, float *sigma, float *acc, float *z,
                        float *pts, int32_t *flags, void *stash, const nafb_loss_tail *tail, cudaStream_t s);
-// the two tensor-core backward kernels: density_bwd_tc.cu (warp-specialised: default) and density_tc.cu (single-role: NAFB_BWD=legacy)
-int nafb_launch_bwd_tc(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
-                       float *grad_table, float *partials, const void *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s);
+// the tensor-core backward kernel (density_bwd_tc.cu)
 int nafb_launch_bwd_ws(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, int src, uint64_t P, const float *dsig,
                        float *grad_table, float *partials, const void *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s);
 
@@ -663,10 +661,7 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
         const MlpLayout lo = make_layout(*mlp);
         long long *stamps = reinterpret_cast<long long *>((char *)workspace + partials_bytes(lo));
         // (the tensor-core kernels reduce the per-CTA MLP gradients themselves, behind a grid-wide barrier: no second launch)
-        static int legacy = -1;   // experiment knob (process-wide, read once): NAFB_BWD=legacy -> the single-role kernel of density_tc.cu
-        if (legacy < 0) { const char *e = getenv("NAFB_BWD"); legacy = e && e[0] == 'l'; }
-        return (legacy ? nafb_launch_bwd_tc : nafb_launch_bwd_ws)(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps,
-                                                                  grid_tc, *grads, s);
+        return nafb_launch_bwd_ws(gp, *mlp, sp, src, P, dsigma_or_dacc, grad_table, (float *)workspace, stash, stamps, grid_tc, *grads, s);
     }
 #define CALL(S_, C_) launch_bwd<S_, C_>(gp, *mlp, sp, P, dsigma_or_dacc, grad_table, *grads, (float *)workspace, s)
     switch (gp.C) {

@@ -671,13 +671,15 @@ int launch_bwd_ws_n(const GridParams &gp, const nafb_mlp &mp, const SamplerParam
     return NAFB_OK;
 }
 
+// Scatter warps per CTA.  Measured at chest_50 (1024 x 192, two CTAs per SM): 4 warps (13 warps x 64 registers) 138 us, 8 warps
+// (17 warps x 56 registers) 124 us; the single-role kernel this one replaced (scatter from the MMA wait slots of the epilogue
+// warps) took 146 us.
+constexpr int SCATTER_WARPS = 8;
+
 template <int SRC, int C>
 int launch_bwd_ws_t(const GridParams &gp, const nafb_mlp &mp, const SamplerParams &sp, uint64_t P, const float *dsig, float *grad_table,
                     float *partials, const uint8_t *stash, long long *stamps, int grid, const nafb_mlp_grads &gr, cudaStream_t s) {
-    static int nsw = 0;   // experiment knob (process-wide, read once): NAFB_BWD_SW = 4 | 8 scatter warps per CTA
-    if (nsw == 0) { const char *e = getenv("NAFB_BWD_SW"); nsw = e && atoi(e) == 8 ? 8 : 4; }
-    return nsw == 8 ? launch_bwd_ws_n<SRC, C, 8>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, grid, gr, s)
-                    : launch_bwd_ws_n<SRC, C, 4>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, grid, gr, s);
+    return launch_bwd_ws_n<SRC, C, SCATTER_WARPS>(gp, mp, sp, P, dsig, grad_table, partials, stash, stamps, grid, gr, s);
 }
 
 }  // namespace

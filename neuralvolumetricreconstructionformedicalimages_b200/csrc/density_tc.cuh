@@ -16,11 +16,6 @@ namespace tc {
 
 
 constexpr int TILE = 128;
-constexpr int NT = 256;
-#ifndef FWD_CTAS
-#define FWD_CTAS 3   // forward CTAs per SM (measured at chest_50: 2 -> 93 us, 3 -> 83 us, 4 -> 125 us: the L1 left over by 4 x 50 KB of shared memory is too small for the coarse levels)
-#endif
-constexpr int NT_B = 288;  // backward: 8 epilogue warps + 1 MMA-issue warp
 constexpr uint32_t LBO = 128;  // bytes between adjacent 8-column chunks of a row group
 
 // ---- weights in shared memory (bf16 hi / lo, rows = output feature, chunks along the input)
@@ -54,61 +49,6 @@ __device__ __forceinline__ void load_weight_images(const nafb_mlp &mp, uint8_t *
         sp->b2[threadIdx.x] = __ldg(mp.b[2] + threadIdx.x);
         sp->w3[threadIdx.x] = __ldg(mp.W[3] + threadIdx.x);
         if (threadIdx.x == 0) sp->b3 = __ldg(mp.b[3]);
-    }
-}
-
-// gather the 16 encoding features [16*half, 16*half+16) of one point into two chunks.
-// The gather is latency-bound (an L2 round trip per level when the loads of one level are all a thread has in flight: ncu
-// shows 0.27 L1TEX wavefronts/clk/SM and 36 % L2 throughput with 44 % of the warp samples waiting on these loads), so the
-// loop is software-pipelined: the loads of level li + GATHER_DEPTH are issued before level li is consumed.
-#ifndef GATHER_DEPTH
-#define GATHER_DEPTH 1
-#endif
-template <int C>
-__device__ __forceinline__ void gather_half(const GridParams &gp, const float (&x01)[3], int half, float (&enc)[16]) {
-    constexpr int LH = 16 / C;  // levels per half
-    float v[LH][8][C];          // fully unrolled: only GATHER_DEPTH + 1 levels are live at any time
-    auto issue = [&](const int li) {
-        const LevelParams lp = gp.lv[half * LH + li];
-        const float *__restrict__ tab = gp.table + (size_t)lp.offset * C;
-        uint32_t g[3];
-        float f[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) locate(x01[d], lp.scale, g[d], f[d]);
-        const uint32_t par = addr_parity8(tab);
-        const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
-        uint32_t e[8];
-        cell_entries8(lp, ct, e);
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j)   // (y, z) corner; the two x-neighbours share one access when adjacent + aligned
-            load_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[li][2 * j], v[li][2 * j + 1]);
-    };
-    auto consume = [&](const int li) {
-        const float scale = gp.lv[half * LH + li].scale;
-        uint32_t g;
-        float f[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) locate(x01[d], scale, g, f[d]);
-        float res[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) res[c] = 0.f;
-#pragma unroll
-        for (uint32_t idx = 0; idx < 8; ++idx) {
-            float w = 1.0f;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (idx & (1u << d)) ? f[d] : __fsub_rn(1.0f, f[d]));
-#pragma unroll
-            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[li][idx][c], res[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) enc[li * C + c] = res[c];
-    };
-#pragma unroll
-    for (int li = 0; li < GATHER_DEPTH && li < LH; ++li) issue(li);
-#pragma unroll
-    for (int li = 0; li < LH; ++li) {
-        if (li + GATHER_DEPTH < LH) issue(li + GATHER_DEPTH);
-        consume(li);
     }
 }
 
@@ -257,36 +197,6 @@ __device__ __forceinline__ void store_half_row(uint8_t *hi, uint8_t *lo, uint32_
 // Behind the two images: a 2 KB tail with what the backward pass would otherwise recompute per point from the ray -- delta_i |d|
 // of the ray integral (render.py:192-201) and the normalised position x01 (hashgrid.py:125): [delta | x | y | z] x 128 fp32.
 constexpr uint32_t ST_SBO = 512, ST_HALF = 8192, ST_ENC = 16384, ST_TAIL_DELTA = ST_ENC, ST_TAIL_X01 = ST_ENC + 512, ST_TILE = ST_ENC + 2048;
-
-__device__ __forceinline__ void store_half_row_and_stash(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo,
-                                                         const float (&v)[16], uint8_t *stash_tile) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint4 h, l;
-        umma::split_chunk(v + 8 * c, h, l);
-        const uint32_t off = umma::canon_off(row, chunk0 + 2 * half + c, LBO, sbo);
-        *reinterpret_cast<uint4 *>(hi + off) = h;
-        *reinterpret_cast<uint4 *>(lo + off) = l;
-        if (stash_tile) {
-            const uint32_t so = umma::canon_off(row, 2 * half + c, LBO, ST_SBO);
-            *reinterpret_cast<uint4 *>(stash_tile + so) = h;   // default policy: the backward pass finds it in L2
-            *reinterpret_cast<uint4 *>(stash_tile + ST_HALF + so) = l;
-        }
-    }
-}
-
-__device__ __forceinline__ void load_stash_half_row(uint8_t *hi, uint8_t *lo, uint32_t row, uint32_t chunk0, int half, uint32_t sbo,
-                                                    const uint8_t *stash_tile) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const uint32_t so = umma::canon_off(row, 2 * half + c, LBO, ST_SBO);
-        const uint4 h = __ldcs(reinterpret_cast<const uint4 *>(stash_tile + so));
-        const uint4 l = __ldcs(reinterpret_cast<const uint4 *>(stash_tile + ST_HALF + so));
-        const uint32_t off = umma::canon_off(row, chunk0 + 2 * half + c, LBO, sbo);
-        *reinterpret_cast<uint4 *>(hi + off) = h;
-        *reinterpret_cast<uint4 *>(lo + off) = l;
-    }
-}
 
 // sign of the stored activations (hi part is enough): slope of LeakyReLU at h
 __device__ __forceinline__ void lrelu_slopes(const uint8_t *hi, uint32_t row, uint32_t chunk0, int half, uint32_t sbo, float (&s)[16]) {

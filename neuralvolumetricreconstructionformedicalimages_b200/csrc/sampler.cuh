@@ -216,9 +216,8 @@ __device__ __forceinline__ float ray_delta(const SamplerParams &sp, const RayReg
 
 // Sample i of ray r AND its ray-integral weight delta_i |d| in one go (what fetch_point + ray_delta evaluate separately): the
 // uniform positions i-1 .. i+2 once, two jitter draws, one ray.  Same operations, same roundings: bit-identical results.
-__device__ __forceinline__ void ray_sample_and_delta(const SamplerParams &sp, uint32_t r, uint32_t i, bool want_delta, float (&x)[3], float &z0,
-                                                     float &delta) {
-    const RayRegs R = load_ray(sp, r);
+__device__ __forceinline__ void ray_sample_and_delta(const SamplerParams &sp, const RayRegs &R, uint32_t r, uint32_t i, bool want_delta,
+                                                     float (&x)[3], float &z0, float &delta) {
     const uint32_t S = sp.n_samples;
     const bool perturb = sp.perturb != 0;
     const Jitter jit = jitter_for(sp, r);
