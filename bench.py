@@ -562,7 +562,7 @@ def main():
     e2e_ms = f0.elapsed_time(f1)
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
     h2d = in_h[0].numel() * 4 + projs_h[0].numel() * 4 + mask_h[0].numel()
-    d2h = 8
+    d2h = 12     # loss, number of valid rays, completion word: written by the forward launch straight into pinned host memory
 
     # the same host entry used the way a training loop would: step k+1 is staged and enqueued before the loss of step k is read
     # (train_step_host(wait=False) -> PendingLoss; every step still copies its inputs H2D and its loss D2H inside the timed region)
@@ -687,7 +687,10 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_wall_ms / K, "device_event_ms_per_step": e2e_ms / K,
-                    "note": "value = synchronous form: every step waits for its own loss before the next one is staged",
+                    "note": "value = synchronous form: every step returns its own loss to the host before the next one is staged; the loss is "
+                            "written by the step's forward launch and polled by the host, so the backward pass and the optimizer of step k "
+                            "overlap the staging, H2D copy (copy stream) and launch of step k+1; the timed region ends with a full device "
+                            "synchronisation",
                     "pipelined": {"value": world * pts_step * K / (piped_wall_ms * 1e-3), "unit": "samples/s", "ms_per_step": piped_wall_ms / K,
                                   "note": "train_step_host(wait=False): the loss of step k is read after step k+1 has been enqueued; "
                                           "same H2D / D2H bytes every step"}},

@@ -198,6 +198,11 @@ typedef struct nafb_loss_tail {
     float *dacc;           /* [n_rays] d loss / d acc                                         */
     int32_t zero_pred;     /* as in nafb_mse_loss                                             */
     uint32_t *ticket;
+    /* optional completion flag (e.g. in pinned, device-mapped host memory): once loss_out is written and visible system-wide the
+     * kernel stores step_state[NAFB_STATE_STEP] + 1 there -- a host thread polling the flag reads the loss of the step without
+     * waiting for the backward pass and the optimizer that follow on the stream.  Both NULL: no flag. */
+    uint32_t *done_flag;
+    const uint32_t *step_state;
 } nafb_loss_tail;
 int nafb_density_forward_loss(const nafb_grid *grid, const nafb_mlp *mlp, const nafb_sampler *smp, float *acc,
                               int32_t *flags, void *stash, const nafb_loss_tail *loss, nafb_stream_t stream);

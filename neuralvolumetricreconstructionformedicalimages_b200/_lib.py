@@ -41,7 +41,8 @@ class Mlp(ctypes.Structure):
 
 class LossTail(ctypes.Structure):
     _fields_ = [("target", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("chunk", u32), ("gscale", ctypes.c_float), ("loss_out", ctypes.c_void_p),
-                ("dacc", ctypes.c_void_p), ("zero_pred", i32), ("ticket", ctypes.c_void_p)]
+                ("dacc", ctypes.c_void_p), ("zero_pred", i32), ("ticket", ctypes.c_void_p), ("done_flag", ctypes.c_void_p),
+                ("step_state", ctypes.c_void_p)]
 
 
 class PixelSource(ctypes.Structure):

@@ -339,7 +339,13 @@ __global__ void __launch_bounds__(128 * NQ, NQ == 2 ? 3 : 2) k_density_fwd_tc(co
             float *s_mean = reinterpret_cast<float *>(smem), *s_cnt = s_mean + MSE_GROUP;   // the operand tiles are dead by now
             const uint32_t n = sp.n_rays, chunk = (tail.chunk == 0 || tail.chunk > n) ? n : tail.chunk;
             mse_loss_block(acc_out, tail.target, tail.mask, n, chunk, tail.gscale, tail.loss_out, tail.dacc, tail.zero_pred, s_mean, s_cnt);
-            if (t == 0) *tail.ticket = 0u;
+            if (t == 0) {
+                *tail.ticket = 0u;
+                if (tail.done_flag) {   // the loss is out: tell a polling host thread (the stores above must be visible first)
+                    __threadfence_system();
+                    *reinterpret_cast<volatile uint32_t *>(tail.done_flag) = tail.step_state ? tail.step_state[NAFB_STATE_STEP] + 1u : 1u;
+                }
+            }
             if (dbg_stamps && t == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)::"memory"); dbg_stamps[237] = (long long)g; }
         }
     }

@@ -250,18 +250,34 @@ def _stage(dst: torch.Tensor, src: torch.Tensor, dtype):
 
 
 class PendingLoss:
-    """The loss of a step enqueued by NAFEngine.train_step_host(wait=False): `result()` waits for that step and returns the float."""
-    __slots__ = ("_event", "_buf", "_value")
+    """The loss of a step enqueued by NAFEngine.train_step_host: `result()` returns the float as soon as the step's FORWARD launch
+    has written it into pinned host memory (it polls the completion word the kernel stores after the loss; the backward pass and
+    the optimizer of the step keep running, stream-ordered before anything enqueued later)."""
+    __slots__ = ("_event", "_buf", "_flag", "_expect", "_value")
 
-    def __init__(self, event, buf):
-        self._event, self._buf, self._value = event, buf, None
+    def __init__(self, event, buf, flag=None, expect=0):
+        self._event, self._buf, self._flag, self._expect, self._value = event, buf, flag, int(expect) & 0xFFFFFFFF, None
 
     def done(self) -> bool:
-        return self._value is not None or self._event.query()
+        if self._value is not None:
+            return True
+        if self._flag is not None:
+            return int(self._flag[0]) == self._expect
+        return self._event.query()
 
     def result(self) -> float:
         if self._value is None:
-            self._event.synchronize()
+            if self._flag is not None:
+                flag, expect = self._flag, self._expect
+                spins = 0
+                while int(flag[0]) != expect:
+                    spins += 1
+                    if spins > 2000000:           # seconds: something is wrong (a launch failed?) -- fall back to the event, which raises
+                        self._event.synchronize()
+                        if int(flag[0]) != expect:
+                            raise RuntimeError("train_step_host: the step finished without writing its loss")
+            else:
+                self._event.synchronize()
             self._value = float(self._buf[0])
         return self._value
 
@@ -417,7 +433,7 @@ class NAFEngine:
             return self.meta.sampler(pixels=pixels.data_ptr(), poses=self.poses.data_ptr(), n_rays=pixels.shape[0], **self.det, **kw)
         return self.meta.sampler(rays=rays.data_ptr(), n_rays=rays.shape[0], **kw)
 
-    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None, stash=None, par=0, pixels=None):
+    def _step_kernels(self, rays, projs, mask, t_rand, loss_out, dacc, acc, timer=None, stash=None, par=0, pixels=None, done_flag=None):
         """density_fwd -> mse_loss -> density_bwd (+ reduce).  t_rand None: the sampler draws its uniforms in-kernel."""
         L_ = _lib.lib()
         tm = timer or _NoTimer()
@@ -434,7 +450,8 @@ class NAFEngine:
             # evaluates the masked chunk-wise MSE and d loss / d acc (nafb_density_forward_loss)
             tail = _lib.LossTail(target=projs.data_ptr(), mask=mask.data_ptr() if mask is not None else None, chunk=chunk, gscale=1.0,
                                  loss_out=loss_out.data_ptr(), dacc=dacc.data_ptr(), zero_pred=1,
-                                 ticket=self.state.data_ptr() + 4 * _lib.STATE_TICKET_FWD)
+                                 ticket=self.state.data_ptr() + 4 * _lib.STATE_TICKET_FWD,
+                                 done_flag=done_flag, step_state=self.state.data_ptr() if done_flag else None)
             with tm("density_fwd_loss"):
                 _lib.check(L_.nafb_density_forward_loss(ctypes.byref(grid), ctypes.byref(mlp), ctypes.byref(smp), _lib.ptr(acc), None, _lib.ptr(stash),
                                                         ctypes.byref(tail), st))
@@ -463,10 +480,10 @@ class NAFEngine:
                                              _lib.ptr(self.exp_avg_sq), self.n_params, self.betas[0], self.betas[1], self.eps,
                                              1.0, 1, _lib.ptr(self.state), _lib.stream_ptr()))
 
-    def _whole_step(self, s, par, timer=None, t_rand=None, with_optimizer=True, use_pixels=False, loss_out=None):
+    def _whole_step(self, s, par, timer=None, t_rand=None, with_optimizer=True, use_pixels=False, loss_out=None, done_flag=None):
         self._step_kernels(None if use_pixels else s["rays"], s["projs"], s["mask"], t_rand, s["loss"] if loss_out is None else loss_out,
                            s["dacc"], s["acc"], timer,
-                           stash=s["stash"], par=par, pixels=s["pixels"] if use_pixels else None)
+                           stash=s["stash"], par=par, pixels=s["pixels"] if use_pixels else None, done_flag=done_flag)
         if with_optimizer:
             self._finish_step(par, timer)
 
@@ -648,13 +665,14 @@ class NAFEngine:
         """One optimisation step fed from HOST memory, result read back to the host: returns the loss as a python float.
 
         The end-to-end form of train_step: the inputs are copied into a pinned staging slot (a few KB of CPU memcpy), and
-        ONE graph launch performs the H2D copy and the whole iteration, whose loss kernel writes the result straight into the
-        slot's pinned host buffer (zero-copy D2H); the call then waits for the stream.  (train_step with pinned host tensors does the same with separate copy calls and leaves
-        the loss on the device.)
+        ONE graph launch performs the H2D copy and the whole iteration.  The forward launch writes the loss straight into the
+        slot's pinned host buffer (zero-copy D2H) followed by a completion word; the call polls that word and returns the loss
+        as soon as the forward pass has produced it -- the backward pass and the optimizer of the step are still running then,
+        stream-ordered before whatever is enqueued next, so the host stages and launches step k+1 while step k finishes and
+        the GPU never drains.  (torch.cuda.synchronize() when the parameters themselves are needed on the host.)
 
-        wait=False returns a PendingLoss instead of waiting: `.result()` gives the float once the step has run.  The staging
-        slots rotate (HOST_SLOTS), so the host can stage and enqueue step k+1 while step k computes -- read the loss of step
-        k after enqueueing step k+1 and the copies and the launch latency disappear behind the kernels."""
+        wait=False returns the PendingLoss instead of polling: `.result()` gives the float.  The staging slots rotate
+        (HOST_SLOTS), so several steps can be in flight."""
         use_pixels = pixels is not None
         src = pixels if use_pixels else rays
         N = src.shape[0]
@@ -665,12 +683,19 @@ class NAFEngine:
         hk = ("host_pix" if use_pixels else "host_rays", slot)
         if s.get(hk) is None:
             hp = torch.zeros(s["packed"].numel(), dtype=torch.uint8).pin_memory()      # host mirror of the packed input buffer
-            loss = torch.zeros(2, dtype=torch.float32).pin_memory()
-            s[hk] = dict(packed=hp, inp=(hp[o_pix:o_pix + 12 * N].view(torch.int32).view(N, 3) if use_pixels
-                                         else hp[o_rays:o_rays + 32 * N].view(torch.float32).view(N, 8)),
+            dp = torch.zeros_like(s["packed"])                                          # ... and the slot's own device copy of it
+            loss = torch.zeros(4, dtype=torch.float32).pin_memory()      # loss, number of valid rays, completion word, pad
+            sv = dict(s)                                                  # the step's buffers with this slot's input block
+            sv.update(packed=dp, rays=dp[o_rays:o_rays + 32 * N].view(torch.float32).view(N, 8),
+                      pixels=dp[o_pix:o_pix + 12 * N].view(torch.int32).view(N, 3), projs=dp[o_projs:o_projs + 4 * N].view(torch.float32),
+                      mask=dp[o_mask:o_mask + N] if mask is not None else None)
+            s[hk] = dict(packed=hp, dev=sv, inp=(hp[o_pix:o_pix + 12 * N].view(torch.int32).view(N, 3) if use_pixels
+                                                 else hp[o_rays:o_rays + 32 * N].view(torch.float32).view(N, 8)),
                          projs=hp[o_projs:o_projs + 4 * N].view(torch.float32), mask=hp[o_mask:o_mask + N],
-                         loss=loss, loss_np=loss.numpy(), event=torch.cuda.Event(), pending=None)
+                         loss=loss, loss_np=loss.numpy(), flag_np=loss.numpy()[2:3].view(np.uint32), event=torch.cuda.Event(),
+                         copied=torch.cuda.Event(), pending=None)
         h = s[hk]
+        sv = h["dev"]
         if h["pending"] is not None:
             h["pending"].result()      # the launch that last used this slot has read its inputs and written its loss
         # staging: a few KB; plain memmove when the caller's tensors already have the staged layout (a torch copy_ call costs
@@ -683,16 +708,27 @@ class NAFEngine:
         with torch.cuda.device(self.device):
             par = self._parity()
             in_graph = not (self.world_size > 1 and self.px is None)
+            # H2D on a copy stream into the slot's own device block: the transfer of step k+1 runs while step k is still
+            # computing (the slot -- and with it this block -- was last used HOST_SLOTS steps ago, and that step has retired:
+            # its successor's loss has been read).  The step's graph waits for the copy's event.
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(self._copy_stream):
+                if use_pixels:     # [pixels | projs | mask] are contiguous: one H2D copy
+                    sv["packed"][o_pix:end].copy_(h["packed"][o_pix:end], non_blocking=True)
+                else:
+                    sv["packed"][o_rays:o_rays + 32 * N].copy_(h["packed"][o_rays:o_rays + 32 * N], non_blocking=True)
+                    sv["packed"][o_projs:end].copy_(h["packed"][o_projs:end], non_blocking=True)
+                h["copied"].record(self._copy_stream)
+            torch.cuda.current_stream().wait_event(h["copied"])
 
             def body(with_optimizer):
-                if use_pixels:     # [pixels | projs | mask] are contiguous: one H2D copy
-                    s["packed"][o_pix:end].copy_(h["packed"][o_pix:end], non_blocking=True)
-                else:
-                    s["packed"][o_rays:o_rays + 32 * N].copy_(h["packed"][o_rays:o_rays + 32 * N], non_blocking=True)
-                    s["packed"][o_projs:end].copy_(h["packed"][o_projs:end], non_blocking=True)
                 # the loss kernel stores its two floats straight into the slot's pinned (device-mapped) host buffer: no D2H copy
                 # node at the end of the graph, and the PCIe write is long done when the backward pass and the optimizer retire
-                self._whole_step(s, par, None, None, with_optimizer=with_optimizer, use_pixels=use_pixels, loss_out=h["loss"])
+                # (the fused forward + loss launch also raises the slot's completion word; without it -- fp32 SIMT arithmetic -- the
+                #  event below is what result() waits for)
+                self._whole_step(sv, par, None, None, with_optimizer=with_optimizer, use_pixels=use_pixels, loss_out=h["loss"],
+                                 done_flag=(h["loss"].data_ptr() + 8) if s["stash"] is not None else None)
 
             shape_key = (N, mask is not None, par, "host", use_pixels)
             key = shape_key + (slot,)
@@ -709,9 +745,10 @@ class NAFEngine:
                 g.replay()
                 if not in_graph:
                     self._finish_step(par)
+            expect = self.step_count + 1          # what the kernel stores: device step count (completed steps) + 1
             self.step_count += 1
             h["event"].record()
-        h["pending"] = PendingLoss(h["event"], h["loss_np"])
+        h["pending"] = PendingLoss(h["event"], h["loss_np"], h["flag_np"] if s["stash"] is not None else None, expect)
         return h["pending"].result() if wait else h["pending"]
 
     def check_health(self):

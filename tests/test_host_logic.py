@@ -278,3 +278,11 @@ def test_host_staging_and_pending_loss_logic():
     assert p.result() == 0.25 and ev.synced == 1 and p.done()
     loss[0] = 9.0                                          # the slot is reused by a later step
     assert p.result() == 0.25 and ev.synced == 1           # cached: no second wait, no stale read
+    # with a completion word (what the fused forward + loss launch stores after the loss): result() polls it, not the event
+    ev2, buf2 = FakeEvent(), np.array([0.5, 7.0, 0.0, 0.0], dtype=np.float32)
+    flag = buf2[2:3].view(np.uint32)
+    p2 = PendingLoss(ev2, buf2, flag, expect=41)
+    flag[0] = 40                                           # an older step's word: not done
+    assert not p2.done()
+    flag[0] = 41
+    assert p2.done() and p2.result() == 0.5 and ev2.synced == 0
