@@ -269,6 +269,17 @@ typedef struct nafb_pixel_source {
 int nafb_draw_pixels(const nafb_pixel_source *src, uint32_t n_rays, int32_t *pixels_out, float *projs_out, uint8_t *mask_out,
                      uint32_t *draw_state, nafb_stream_t stream);
 
+/* ------------------------------------------------------------------ evaluation metrics (reference train.py:253-258)
+ * Float64 arithmetic like the reference's numpy code; both kernels leave one partial sum per block (n_partial blocks of 256
+ * threads, summed in block order by the caller: deterministic), nothing is copied to the host but those few doubles.
+ * nafb_sqdiff_f64: sum (a - b)^2  ->  get_psnr_3d = 20 log10(PIXEL_MAX / sqrt(sum / n))           (src/utils/util.py:55-84).
+ * nafb_ssim3d_f64: sum over the interior of the local SSIM of two [n1,n2,n3] volumes -- uniform win^3 window, sample covariance,
+ * K1 0.01, K2 0.03, C = (K data_range)^2: what skimage.metrics.structural_similarity computes for a 3-D float array without a
+ * channel axis; get_ssim_3d = sum / ((n1-win+1)(n2-win+1)(n3-win+1))                                  (src/utils/util.py:87-139). */
+int nafb_sqdiff_f64(const float *a, const float *b, uint64_t n, double *partial, uint32_t n_partial, nafb_stream_t stream);
+int nafb_ssim3d_f64(const float *a, const float *b, uint32_t n1, uint32_t n2, uint32_t n3, uint32_t win, double data_range,
+                    double *partial, uint32_t n_partial, nafb_stream_t stream);
+
 /* ------------------------------------------------------------------ optimiser
  * torch.optim.Adam (trainer.py:54: betas (0.9,0.999), eps 1e-8, no weight decay, no amsgrad),
  * one fused pass over a flat parameter vector; grad is zeroed in the same pass when zero_grad != 0

@@ -105,6 +105,8 @@ _SIGNATURES = {
     "nafb_ray_integral_forward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_ray_integral_backward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_mse_loss": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, u32, u32, ctypes.c_float, c_f32p, c_f32p, ctypes.c_int, ctypes.c_void_p]),
+    "nafb_sqdiff_f64": (ctypes.c_int, [c_f32p, c_f32p, u64, ctypes.c_void_p, u32, ctypes.c_void_p]),
+    "nafb_ssim3d_f64": (ctypes.c_int, [c_f32p, c_f32p, u32, u32, u32, u32, ctypes.c_double, ctypes.c_void_p, u32, ctypes.c_void_p]),
     "nafb_ptycho_mask": (ctypes.c_int, [c_f32p, u32, u32, u32, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "nafb_draw_pixels": (ctypes.c_int, [ctypes.POINTER(PixelSource), u32, ctypes.c_void_p, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nafb_density_forward_loss": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), c_f32p, ctypes.c_void_p, ctypes.c_void_p,

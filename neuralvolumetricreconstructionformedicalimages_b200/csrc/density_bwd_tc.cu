@@ -140,8 +140,11 @@ __global__ void __launch_bounds__(bound_threads(NSW), 2) k_density_bwd_ws(const 
     kstamp(0);
     load_weight_images(mp, W_hi, W_lo, small);
     if (t < NAFB_MAX_LEVELS) lvs[t] = gp.lv[t];
-    // operand buffers start finite: the stacked 128-feature window of the dW products reads rows that are never written
-    for (uint32_t i = t; i < (2 * ENC_BYTES + AH_BYTES + AL_BYTES) / 16; i += NTW) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    // The stacked 128-feature window of the dW products (A = [G_hi | G_lo | 64 more rows]) reads, beyond G, the H0 / H1 chunks of
+    // the NEXT row group -- written by the epilogue before the first dW product -- and, for the last row group, the 1 KB of slack
+    // behind the buffer: that slack is the only operand memory no role ever writes, so it is what gets cleared (the rows it feeds,
+    // TMEM lanes 64-127 of the dW accumulators, are never read back; they only have to stay finite).
+    for (uint32_t i = t; i < 1024 / 16; i += NTW) reinterpret_cast<uint4 *>(A_hi + 16 * AH_SBO)[i] = make_uint4(0, 0, 0, 0);
     if (t == 0) {
         umma::mbar_init(&ctl->mma, 1);
         umma::mbar_init(&ctl->dw, 1);

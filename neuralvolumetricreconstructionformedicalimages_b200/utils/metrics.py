@@ -1,5 +1,7 @@
-"""Evaluation metrics of the reference (src/utils/util.py:18-139), computed where the data lives (torch ops on the
-tensors' own device, float64 like the reference's numpy code) -- no device->host copy of the volume, no skimage.
+"""Evaluation metrics of the reference (src/utils/util.py:18-139), computed where the data lives, float64 like the
+reference's numpy code -- no device->host copy of the volume, no skimage.  The two 3-D metrics of eval_step (train.py:253-258) run
+as CUDA kernels of the library (csrc/metrics.cu) for fp32 volumes on the GPU; host-side / other-dtype inputs (the CPU test suite,
+float64 fixtures) evaluate the same formulas with torch ops.
 
 get_ssim_3d restates what the reference obtains from ``skimage.metrics.structural_similarity`` on a 3-D array without a
 channel axis (util.py:87-139): the N-dimensional SSIM of Wang et al. with a uniform 7x7x7 window, K1 = 0.01, K2 = 0.03,
@@ -33,21 +35,51 @@ def get_psnr(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return -10.0 * torch.log10(get_mse(xn, yn))
 
 
+def _on_device(arr1, arr2):
+    return (arr1.is_cuda and arr2.is_cuda and arr1.device == arr2.device and arr1.dtype == torch.float32 and arr2.dtype == torch.float32
+            and arr1.shape == arr2.shape)
+
+
 def get_psnr_3d(arr1: torch.Tensor, arr2: torch.Tensor, PIXEL_MAX: float = 1.0) -> float:
-    """util.py:55-84 for one volume: 20 log10(PIXEL_MAX / sqrt(mse)) in float64; 100 when the volumes are identical."""
-    a, b = arr1.detach().to(torch.float64), arr2.detach().to(torch.float64)
-    mse = torch.mean((a - b) ** 2)
-    if float(mse) == 0.0:
+    """util.py:55-84 for one volume: 20 log10(PIXEL_MAX / sqrt(mse)) in float64; 100 when the volumes are identical.
+    fp32 CUDA volumes: one reduction kernel (nafb_sqdiff_f64); anything else: the same arithmetic with torch ops."""
+    if _on_device(arr1, arr2):
+        import ctypes
+        from .. import _lib
+        a, b = arr1.detach().contiguous(), arr2.detach().contiguous()
+        nb = 1024
+        part = torch.empty(nb, dtype=torch.float64, device=a.device)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.lib().nafb_sqdiff_f64(_lib.ptr(a), _lib.ptr(b), a.numel(), _lib.ptr(part), nb, _lib.stream_ptr()))
+        mse = float(part.cpu().numpy().sum()) / a.numel()       # block order: deterministic
+    else:
+        a, b = arr1.detach().to(torch.float64), arr2.detach().to(torch.float64)
+        mse = float(torch.mean((a - b) ** 2))
+    if mse == 0.0:
         return 100.0
-    return float(20.0 * torch.log10(PIXEL_MAX / torch.sqrt(mse)))
+    import math
+    return 20.0 * math.log10(PIXEL_MAX / math.sqrt(mse))
 
 
 def get_ssim_3d(arr1: torch.Tensor, arr2: torch.Tensor, data_range: float = 2.0, win_size: int = 7) -> float:
-    """util.py:87-139 for one [D,H,W] volume (see the module docstring)."""
+    """util.py:87-139 for one [D,H,W] volume (see the module docstring).  fp32 CUDA volumes: one kernel that evaluates every
+    window directly in float64 (nafb_ssim3d_f64); anything else: the same statistic with torch pooling ops."""
+    if arr1.dim() != 3 or arr1.shape != arr2.shape:
+        raise ValueError("get_ssim_3d: two [D,H,W] volumes of the same shape expected")
+    if min(arr1.shape) < win_size:
+        raise ValueError("win_size exceeds image extent")
+    if _on_device(arr1, arr2):
+        from .. import _lib
+        a, b = arr1.detach().contiguous(), arr2.detach().contiguous()
+        n1, n2, n3 = [int(v) for v in a.shape]
+        nb = 2048
+        part = torch.empty(nb, dtype=torch.float64, device=a.device)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.lib().nafb_ssim3d_f64(_lib.ptr(a), _lib.ptr(b), n1, n2, n3, int(win_size), float(data_range), _lib.ptr(part), nb,
+                                                  _lib.stream_ptr()))
+        return float(part.cpu().numpy().sum()) / ((n1 - win_size + 1) * (n2 - win_size + 1) * (n3 - win_size + 1))
     a = arr1.detach().to(torch.float64)[None, None]
     b = arr2.detach().to(torch.float64)[None, None]
-    if min(a.shape[2:]) < win_size:
-        raise ValueError("win_size exceeds image extent")
     NP = win_size ** 3
     cov_norm = NP / (NP - 1.0)
     pool = lambda t: F.avg_pool3d(t, win_size, stride=1)      # uniform filter restricted to the interior == filter + crop

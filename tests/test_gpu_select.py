@@ -121,3 +121,22 @@ def test_draw_pixels_is_uniform_without_replacement():
     both = np.mean([(a in r) and (b in r) for r in (set(x) for x in flat.tolist())])
     expect = N * (N - 1) / (M * (M - 1))
     assert abs(both - expect) < 5 * np.sqrt(expect * (1 - expect) / K), (both, expect)
+
+
+def test_metric_kernels_vs_oracle():
+    """get_psnr_3d / get_ssim_3d on fp32 CUDA volumes (csrc/metrics.cu; reference src/utils/util.py:55-139, eval_step train.py:253-258)
+    against the oracle's float64 numpy / scipy restatements (themselves pinned to the reference's PSNR fixture and to a brute-force
+    evaluation of the published SSIM definition in tests/test_host_logic.py)."""
+    from neuralvolumetricreconstructionformedicalimages_b200.utils import get_psnr_3d, get_ssim_3d
+    rng = np.random.default_rng(3)
+    for shape in ((20, 17, 23), (7, 7, 7), (64, 64, 64), (9, 40, 8)):
+        v1 = rng.uniform(0, 1, shape).astype(np.float32)
+        v2 = np.clip(v1 + rng.normal(0, 0.05, shape), 0, 1).astype(np.float32)
+        a, b = torch.from_numpy(v1).to(DEV), torch.from_numpy(v2).to(DEV)
+        assert abs(get_psnr_3d(a, b) - naf.psnr_3d(v1, v2)) < 1e-9
+        assert abs(get_ssim_3d(a, b) - naf.ssim_3d(v1, v2)) < 1e-10, shape
+        assert get_psnr_3d(a, a) == 100.0 and abs(get_ssim_3d(a, a) - 1.0) < 1e-12
+        # the torch-op path (what host-side float64 inputs take) agrees with the kernels
+        assert abs(get_ssim_3d(a.double(), b.double()) - get_ssim_3d(a, b)) < 1e-10
+    with pytest.raises(ValueError):
+        get_ssim_3d(torch.zeros(6, 9, 9, device=DEV), torch.zeros(6, 9, 9, device=DEV))
