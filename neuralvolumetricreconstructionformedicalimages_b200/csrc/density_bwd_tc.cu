@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(bound_threads(NSW), 2) k_density_bwd_ws(const 
         // columns -- units of 16 columns x 18 row slices; a slice adds its rows in order with four loads in flight, the slice
         // sums are added in order: the summation tree is a function of the grid size only (deterministic).
         // sync[0] counts arrivals, sync[1] departures; the last CTA to leave clears both (the workspace starts zero-filled).
-        // A CTA that has waited 30 s raises sync[2] (the host reads it: NAFEngine.check_health) and leaves without reducing.
+        // A CTA that has waited 10 s raises sync[2] (the host reads it: NAFEngine.check_health) and leaves without reducing.
         if (sync != nullptr) {
             __shared__ uint32_t s_ok;
             __threadfence();
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(bound_threads(NSW), 2) k_density_bwd_ws(const 
                     unsigned long long now;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                     if (t0 == 0) t0 = now;
-                    if (now - t0 > 30000000000ull) {   // a CTA of this grid never became resident
+                    if (now - t0 > 10000000000ull) {   // 10 s: a CTA of this grid never became resident
                         atomicExch(sync + 2, 1u);
                         s_ok = 0u;
                         break;

@@ -206,3 +206,50 @@ def test_two_gpu_peer_exchange_matches_nccl(tmp_path):
     # two ranks == one GPU on the concatenated batch (replicas start from rank 0's parameters in both runs)
     a, b = res["nccl"]["param"].numpy(), res["solo"]["param"].numpy()
     assert (np.abs(a - b) > 5e-5).mean() < 1e-4 and np.abs(a - b).max() < 2.1e-3 * 5   # 5 steps of lr 1e-3; float-atomic order differs
+
+
+def test_backward_grid_barrier_survives_a_busy_gpu():
+    """The tensor-core backward kernel reduces the per-CTA MLP gradients behind a grid-wide barrier of its own (cooperative launch
+    is not available to kernels that allocate tensor memory: the occupancy API answers 1 CTA per SM for them).  Its CTAs must all
+    become resident, so a long kernel on ANOTHER stream may delay part of the grid while the rest spins: the launch has to finish
+    (no trap, no time-out flag) with the same result as on a quiet GPU, and two engines stepping on two streams at once -- each
+    with its own workspace -- must not disturb each other."""
+    dev = torch.device("cuda", 0)
+    batches, S = _batches(3, 3, N=1024, S=192)
+
+    def run(eng, busy):
+        side = torch.cuda.Stream(device=dev)
+        a = torch.randn(8192, 8192, device=dev)
+        out = []
+        for rays, projs, t_rand in batches:
+            if busy:
+                with torch.cuda.stream(side):          # ~10 ms of work that fills every SM while the step is enqueued
+                    for _ in range(12):
+                        a = (a @ a).clamp_(-1, 1)
+            out.append(float(eng.train_step(rays.to(dev), projs.to(dev), None, t_rand.to(dev))))
+        torch.cuda.synchronize()
+        eng.check_health()
+        return out, eng.flat_param.clone()
+
+    quiet, p_quiet = run(NAFEngine(_net(dev), lr=1e-3, n_samples=S, perturb=True, loss_chunk=200, use_cuda_graph=False), busy=False)
+    loud, p_loud = run(NAFEngine(_net(dev), lr=1e-3, n_samples=S, perturb=True, loss_chunk=200, use_cuda_graph=False), busy=True)
+    np.testing.assert_allclose(loud, quiet, rtol=1e-5)
+    assert float((p_loud - p_quiet).abs().max()) < 5e-5      # float-atomic order differs from run to run, nothing else
+    # two engines, two streams, at the same time
+    e1 = NAFEngine(_net(dev), lr=1e-3, n_samples=S, perturb=True, loss_chunk=200, use_cuda_graph=False)
+    e2 = NAFEngine(_net(dev), lr=1e-3, n_samples=S, perturb=True, loss_chunk=200, use_cuda_graph=False)
+    assert e1._bwd_ws.data_ptr() != e2._bwd_ws.data_ptr()
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    dev_batches = [(r.to(dev), p.to(dev), t.to(dev)) for r, p, t in batches]
+    torch.cuda.synchronize()
+    l1, l2 = [], []
+    for rays, projs, t_rand in dev_batches:
+        with torch.cuda.stream(s1):
+            l1.append(e1.train_step(rays, projs, None, t_rand).clone())       # (the returned scalar is a view of a buffer the next step overwrites)
+        with torch.cuda.stream(s2):
+            l2.append(e2.train_step(rays, projs, None, t_rand).clone())
+    torch.cuda.synchronize()
+    e1.check_health()
+    e2.check_health()
+    np.testing.assert_allclose([float(v) for v in l1], quiet, rtol=1e-5)
+    np.testing.assert_allclose([float(v) for v in l2], quiet, rtol=1e-5)
