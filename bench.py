@@ -582,6 +582,25 @@ def main():
     barrier()
     piped_wall_ms = 1e3 * (time.perf_counter() - t0)
 
+    # ---------------- the same step with the batch DRAWN ON THE DEVICE inside the graph (NAFEngine.train_step_sampled: the reference's
+    # per-iteration dataset work, tigre.py:354-382, as a kernel of the step): no per-step host input at all
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset.mask import PixelSampler
+    gen_s = torch.Generator(device=device).manual_seed(4321 + rank)
+    ps = PixelSampler(torch.rand(N_PROJ, DET, DET, device=device, generator=gen_s) * 0.05 + 1e-4,
+                      torch.polar(torch.where(torch.rand(N_PROJ, DET, DET, device=device, generator=gen_s) < 0.02, 0.003, 1.0),
+                                  torch.zeros(N_PROJ, DET, DET, device=device)), 0.007, seed=99 + rank)
+    for i in range(5):
+        eng.train_step_sampled(ps, N_RAYS)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(K):
+        sampled_loss = eng.train_step_sampled(ps, N_RAYS)
+    g1.record()
+    barrier()
+    sampled_ms = g0.elapsed_time(g1)
+    ps.check()
+
     # ---------------- per-kernel CUDA-event timing (instrumented eager pass, same workload)
     from neuralvolumetricreconstructionformedicalimages_b200.engine import EventTimer
     timer = EventTimer()
@@ -607,10 +626,10 @@ def main():
     loss_all = float(parallel.combined_loss(loss, eng.pg).item())
 
     # ---------------- reduce over ranks (max time)
-    t = torch.tensor([ms, e2e_wall_ms, piped_wall_ms], device=device, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_wall_ms, piped_wall_ms, sampled_ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_wall_ms, piped_wall_ms = float(t[0]), float(t[1]), float(t[2])
+    ms, e2e_wall_ms, piped_wall_ms, sampled_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     pts_step = N_RAYS * N_SAMPLES
     value = world * pts_step * K / (ms * 1e-3)
     e2e_value = world * pts_step * K / (e2e_wall_ms * 1e-3)
@@ -694,6 +713,9 @@ def main():
                     "pipelined": {"value": world * pts_step * K / (piped_wall_ms * 1e-3), "unit": "samples/s", "ms_per_step": piped_wall_ms / K,
                                   "note": "train_step_host(wait=False): the loss of step k is read after step k+1 has been enqueued; "
                                           "same H2D / D2H bytes every step"}},
+            "sampled": {"value": world * pts_step * K / (sampled_ms * 1e-3), "unit": "samples/s", "ms_per_step": sampled_ms / K,
+                        "note": "NAFEngine.train_step_sampled: the pixel draw of the reference's dataset (non-zero pixels, without replacement, "
+                                "mask lookup) is a kernel inside the step's CUDA graph; projections resident, 4 launches per step"},
             "gpu_launches": eng.launches_per_step * K,
             "roofline": roofline,
             "kernels": kernels,

@@ -56,8 +56,7 @@ def main():
     rays_all = G.rays_with_near_far(data["angles"], geo, "cpu")
     projs = PH.phantom_projections(rays_all, ells).to(dev)                      # [50, 256, 256] exact line integrals
     del rays_all
-    sampler = PixelSampler(projs)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    sampler = PixelSampler(projs, seed=1234 + rank)
 
     enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
     net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(dev)
@@ -69,16 +68,15 @@ def main():
         return get_psnr_3d(vol, vol_gt), get_ssim_3d(vol, vol_gt)
 
     n_proj = projs.shape[0]
-    order = np.random.default_rng(0)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     it = 0
     for epoch in range(args.epochs):
         eng.lr = 1e-3 * (0.1 ** (epoch // args.lrate_step))                    # StepLR(step_size in epochs, gamma 0.1), trainer.py:57
-        # the epoch's 50 batches in a few batched device ops (dataset/mask.py), then 50 graph launches
-        pix_e, tgt_e, msk_e = sampler.draw_epoch(args.n_rays, gen, projections=order.permutation(n_proj))
+        # one pass over the projections in the order of the reference's un-shuffled DataLoader: every iteration is ONE graph launch --
+        # pixel draw on the device (csrc/select.cu), forward + loss, backward, Adam -- with no per-step host input at all
         for k in range(n_proj):
-            loss = eng.train_step(None, tgt_e[k], msk_e[k], pixels=pix_e[k])
+            loss = eng.train_step_sampled(sampler, args.n_rays)
             it += 1
         if args.eval_every and (epoch + 1) % args.eval_every == 0 and rank == 0:
             psnr, ssim = evaluate()

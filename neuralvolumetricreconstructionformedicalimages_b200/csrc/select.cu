@@ -7,9 +7,9 @@
 //
 // Uniform sampling without replacement = the n smallest of i.i.d. random keys, in key order (a uniformly random ordered
 // subset, the distribution of np.random.choice(replace=False)).  Keys are counter-based: hash(seed, draw, candidate) -- no
-// state per candidate, the same draw for the same (seed, draw counter).  One CTA: a 3-pass radix select over the 32 key bits
-// finds the n-th smallest key, the selected (key, candidate) pairs are compacted into shared memory and bitonic-sorted, so
-// the output order does not depend on the order the atomics were served in.
+// state per candidate, the same draw for the same (seed, draw counter).  One CTA, one pass over the candidates: those whose key
+// lies below a threshold just above the expected n-th smallest key are collected in shared memory and bitonic-sorted; the first n
+// are the draw, so neither the set nor the order depends on the order the atomics were served in.
 #include "common.cuh"
 
 namespace {
@@ -19,7 +19,17 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
-__device__ __forceinline__ uint32_t draw_key(uint64_t stream_key, uint32_t j) { return (uint32_t)(mix64(stream_key + (uint64_t)j * 0x9E3779B97F4A7C15ull) >> 32); }
+// 32-bit key of candidate j in the stream (seed, draw): two rounds of an integer finaliser (full avalanche), a dozen instructions --
+// the draw kernel is ONE CTA whose time is the hashing of every candidate
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t draw_key(uint64_t stream_key, uint32_t j) {
+    return mix32(mix32(j ^ (uint32_t)stream_key) + (uint32_t)(stream_key >> 32));
+}
 
 // m = |hr| < thr; m[1:, :] &= (m[1:, :] == m[:-1, :]); m[:, 1:] &= (m[:, 1:] == m[:, :-1]); keep = ~m
 // (each right-hand side is evaluated on the mask as it was BEFORE that statement, as torch does).
@@ -44,7 +54,7 @@ __global__ void __launch_bounds__(256) k_ptycho_mask(const float2 *__restrict__ 
 }
 
 constexpr int DRAW_THREADS = 1024;
-constexpr uint32_t DRAW_MAX = 8192;    // rays per draw (pairs sorted in shared memory: 64 KB)
+constexpr uint32_t DRAW_MAX = 8192;    // rays per draw (up to 2 x 8192 candidate pairs in shared memory: 128 KB)
 
 struct DrawParams {
     const float *projs;        // [P, H*W]
@@ -63,8 +73,7 @@ struct DrawParams {
 __global__ void __launch_bounds__(DRAW_THREADS) k_draw_pixels(const DrawParams D) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t *pairs = reinterpret_cast<uint64_t *>(smem_raw);             // [n_pow2] (key << 32 | candidate)
-    __shared__ uint32_t hist[2048];
-    __shared__ uint32_t s_bin, s_rank, s_count, s_ties;
+    __shared__ uint32_t s_count;
     const uint32_t t = threadIdx.x;
     const uint32_t draw = D.state[0];
     const uint64_t seed = (uint64_t)D.state[1] | ((uint64_t)D.state[2] << 32);
@@ -78,71 +87,49 @@ __global__ void __launch_bounds__(DRAW_THREADS) k_draw_pixels(const DrawParams D
     if (M < n) {   // fewer valid pixels than rays: the reference's np.random.choice raises; flag it and emit the first pixels
         if (t == 0) D.state[3] = 1u + p;
     }
-    // ---- radix select: prefix of the n-th smallest key, 11 + 11 + 10 bits
-    uint32_t prefix = 0, prefix_bits = 0, want = n < M ? n : M;   // `want`-th smallest (1-based) among keys matching the prefix
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t bits = pass < 2 ? 11u : 10u, shift = 32u - prefix_bits - bits;
-        for (uint32_t i = t; i < 2048; i += DRAW_THREADS) hist[i] = 0;
+    // ---- ONE pass: the keys are uniform, so the n-th smallest sits near n / M * 2^32; every candidate whose key is below a threshold
+    // six standard deviations above that is collected (n + 6 sqrt(n) + 8 of them on average) and the n smallest are kept by the
+    // sort below.  Should the list come out short (probability ~ 1e-9) or overflow, the threshold is adjusted and the pass repeated.
+    const uint32_t n_out = n < M ? n : M;
+    const uint32_t cap = 2u * n_pow2;                       // pairs that fit in shared memory
+    const double want_cnt = (double)n_out + 6.0 * sqrt((double)n_out) + 8.0;
+    uint32_t T = want_cnt >= (double)M ? 0xffffffffu : (uint32_t)(want_cnt / (double)M * 4294967296.0);
+    for (int attempt = 0; attempt < 40; ++attempt) {
+        if (t == 0) s_count = 0;
+        for (uint32_t i = t; i < cap; i += DRAW_THREADS) pairs[i] = ~0ull;
         __syncthreads();
-        for (uint32_t j = t; j < M; j += DRAW_THREADS) {
-            const uint32_t k = draw_key(skey, j);
-            if (prefix_bits == 0 || (k >> (32u - prefix_bits)) == prefix) atomicAdd(&hist[(k >> shift) & ((1u << bits) - 1u)], 1u);
-        }
-        __syncthreads();
-        if (t == 0) {
-            uint32_t cum = 0, b = 0;
-            for (; b < (1u << bits); ++b) {
-                if (cum + hist[b] >= want) break;
-                cum += hist[b];
+        for (uint32_t jj = t; jj < M; jj += DRAW_THREADS) {
+            const uint32_t k = draw_key(skey, jj);
+            if (k <= T) {
+                const uint32_t q = atomicAdd(&s_count, 1u);
+                if (q < cap) pairs[q] = ((uint64_t)k << 32) | jj;
             }
-            s_bin = b;
-            s_rank = want - cum;
         }
         __syncthreads();
-        prefix = (prefix << bits) | s_bin;
-        prefix_bits += bits;
-        want = s_rank;
+        const uint32_t got = s_count;
         __syncthreads();
+        if (got >= n_out && got <= cap) break;
+        T = got < n_out ? (T >= 0x7fffffffu ? 0xffffffffu : 2u * T + 1u) : T - T / 4u;   // too few: widen; overflow: narrow
     }
-    const uint32_t T = prefix;          // the n-th smallest key; `want` of the candidates whose key equals T are taken (lowest index first)
-    // ---- compaction of (key, candidate); candidates whose key EQUALS the threshold (rare with 32-bit keys) go to a side list
-    __shared__ uint32_t tie_list[64];
-    if (t == 0) { s_count = 0; s_ties = 0; }
-    for (uint32_t i = t; i < n_pow2; i += DRAW_THREADS) pairs[i] = ~0ull;
-    __syncthreads();
-    for (uint32_t j = t; j < M; j += DRAW_THREADS) {
-        const uint32_t k = draw_key(skey, j);
-        if (k < T) pairs[atomicAdd(&s_count, 1u)] = ((uint64_t)k << 32) | j;
-        else if (k == T) { const uint32_t q = atomicAdd(&s_ties, 1u); if (q < 64u) tie_list[q] = j; }
+    // ---- bitonic sort of the collected pairs (padding = ~0 sorts last): position i of the batch gets the i-th smallest key -- a
+    // uniformly random ORDER as well, independent of the order the atomics above were served in
+    uint32_t sort_n = 1;
+    {
+        const uint32_t got = s_count < cap ? s_count : cap;
+        while (sort_n < got) sort_n <<= 1;
     }
-    __syncthreads();
-    if (t == 0) {   // take `want` of the ties, lowest candidate index first (insertion sort of a handful of entries)
-        const uint32_t nt = s_ties < 64u ? s_ties : 64u;
-        for (uint32_t a = 1; a < nt; ++a) {
-            const uint32_t v = tie_list[a];
-            uint32_t b = a;
-            for (; b > 0 && tie_list[b - 1] > v; --b) tie_list[b] = tie_list[b - 1];
-            tie_list[b] = v;
-        }
-        for (uint32_t a = 0; a < want && a < nt; ++a) pairs[s_count + a] = ((uint64_t)T << 32) | tie_list[a];
-    }
-    __syncthreads();
-    // ---- bitonic sort of n_pow2 pairs (padding = ~0 sorts last)
-    for (uint32_t k = 2; k <= n_pow2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = t; i < n_pow2; i += DRAW_THREADS) {
-                const uint32_t l = i ^ j;
-                if (l > i) {
-                    const uint64_t a = pairs[i], b = pairs[l];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { pairs[i] = b; pairs[l] = a; }
-                }
+    for (uint32_t k = 2; k <= sort_n; k <<= 1) {
+        for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+            for (uint32_t c = t; c < (sort_n >> 1); c += DRAW_THREADS) {     // comparator c works on (i, i + jj), bit jj of i clear
+                const uint32_t i = 2u * c - (c & (jj - 1u)), l = i + jj;
+                const uint64_t a = pairs[i], b = pairs[l];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { pairs[i] = b; pairs[l] = a; }
             }
             __syncthreads();
         }
     }
     // ---- gather
-    const uint32_t n_out = n < M ? n : M;
     for (uint32_t i = t; i < n; i += DRAW_THREADS) {
         const uint32_t j = i < n_out ? (uint32_t)(pairs[i] & 0xffffffffu) : (M ? i % M : 0u);
         const uint32_t pix = M ? (uint32_t)__ldg(cand + j) : 0u;
@@ -183,9 +170,9 @@ int nafb_draw_pixels(const nafb_pixel_source *src, uint32_t n_rays, int32_t *pix
     D.pixels_out = pixels_out; D.projs_out = projs_out; D.mask_out = mask_out; D.state = draw_state;
     uint32_t n_pow2 = 1;
     while (n_pow2 < n_rays) n_pow2 <<= 1;
-    const size_t smem = (size_t)n_pow2 * sizeof(uint64_t);
+    const size_t smem = (size_t)2 * n_pow2 * sizeof(uint64_t);
     static bool configured[NAFB_MAX_DEVICES] = {};
-    NAFB_CONFIGURE_SMEM(configured, k_draw_pixels, DRAW_MAX * sizeof(uint64_t), "draw_pixels");
+    NAFB_CONFIGURE_SMEM(configured, k_draw_pixels, 2 * DRAW_MAX * sizeof(uint64_t), "draw_pixels");
     k_draw_pixels<<<1, DRAW_THREADS, smem, (cudaStream_t)stream>>>(D);
     NAFB_CHECK_LAUNCH("draw_pixels");
     return NAFB_OK;

@@ -140,3 +140,47 @@ def test_metric_kernels_vs_oracle():
         assert abs(get_ssim_3d(a.double(), b.double()) - get_ssim_3d(a, b)) < 1e-10
     with pytest.raises(ValueError):
         get_ssim_3d(torch.zeros(6, 9, 9, device=DEV), torch.zeros(6, 9, 9, device=DEV))
+
+
+def test_train_step_sampled_equals_draw_then_train_step():
+    """NAFEngine.train_step_sampled (draw kernel + forward/loss + backward + optimizer in ONE CUDA graph, no per-step host input)
+    performs exactly the steps of `sampler.draw_into(...)` followed by `train_step(pixels=...)` on a twin engine with the same seeds:
+    same pixels, same in-kernel uniforms, so losses agree to the order of the float atomics."""
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import geometry as G
+    from neuralvolumetricreconstructionformedicalimages_b200.dataset import phantom as PH
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder import get_encoder
+    from neuralvolumetricreconstructionformedicalimages_b200.engine import NAFEngine
+    from neuralvolumetricreconstructionformedicalimages_b200.network import get_network
+    data = G.chest50_like(n_voxel=32, n_detector=64, n_proj=5)
+    geo = G.ConeGeometry(data)
+    ells = PH.default_ellipsoids(float(geo.sVoxel[0]) / 2)
+    projs = PH.phantom_projections(G.rays_with_near_far(data["angles"], geo, "cpu"), ells).to(DEV)
+    # 8x8 BLOCKS of low amplitude: the ptycho rule compares finite differences, an isolated low pixel is not masked
+    low = (torch.rand(projs.shape[0], projs.shape[1] // 8, projs.shape[2] // 8, device=DEV) < 0.3)
+    low = low.repeat_interleave(8, 1).repeat_interleave(8, 2)
+    full = torch.polar(torch.where(low, 0.003, 1.0), projs)
+
+    def engine():
+        torch.manual_seed(0)
+        enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
+        net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(DEV)
+        eng = NAFEngine(net, lr=1e-3, n_samples=64, perturb=True, loss_chunk=100, use_cuda_graph=True, seed=7)
+        eng.set_geometry(data["angles"], geo)
+        return eng
+
+    N = 512
+    e1, e2 = engine(), engine()
+    s1, s2 = PixelSampler(projs, full, 0.007, seed=3), PixelSampler(projs, full, 0.007, seed=3)
+    pix = torch.empty(N, 3, dtype=torch.int32, device=DEV)
+    val = torch.empty(N, device=DEV)
+    msk = torch.empty(N, dtype=torch.uint8, device=DEV)
+    for k in range(7):                                    # eager first, then captured + replayed
+        l1 = float(e1.train_step_sampled(s1, N))
+        s2.draw_into(N, pix, val, msk)
+        assert bool((pix[:, 0] == k % 5).all()) and 0 < int(msk.sum()) < N
+        l2 = float(e2.train_step(None, val.clone(), msk.clone(), pixels=pix.clone()))
+        np.testing.assert_allclose(l1, l2, rtol=1e-5)
+    assert s1.draws_done() == 7 and e1.step_count == 7
+    s1.check()
+    e1.check_health()
+    assert float((e1.flat_param - e2.flat_param).abs().max()) < 5e-5
