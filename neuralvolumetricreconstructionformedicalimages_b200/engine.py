@@ -105,7 +105,7 @@ class PeerExchange:
               stores only over NVLink, one gradient buffer per rank (the default: fastest measured).
     """
 
-    FLAG_BYTES = 256
+    FLAG_BYTES = 1024                  # >= 4 * _lib.XFLAG_WORDS; keeps the vectors behind it 256-byte aligned
 
     def __init__(self, n, device, group, rank, world, backend="ipc"):
         """Set-up is COLLECTIVE and staged so that a failure on one rank never leaves the others inside a collective that
@@ -198,6 +198,7 @@ class PeerExchange:
                     x.stage[w] = base + stage_off
             if backend == "push":
                 x.stage_slot = slot
+                x.push_chunks = int(os.environ.get("NAFB_PUSH_CHUNKS", "0"))    # 0: the library's default (8); for sweeps
             else:
                 x.grad_zero = local_ptr + fb + (1 + (1 - par)) * seg
             x.exp_avg, x.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
