@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 10
+#define NAFB_ABI_VERSION 9
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -307,13 +307,8 @@ int nafb_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
 #define NAFB_XFLAG_DONE 8     /* [8..15] written by rank i: "I have finished writing your parameters"          */
 #define NAFB_XFLAG_ERROR 16   /* != 0: a spin timed out (value - 1 = index of the flag that never arrived)     */
 #define NAFB_XFLAG_TICKET 17  /* local block counter                                                           */
-#define NAFB_XFLAG_TICKET2 18 /* local block counter of the push edition (blocks that have left the task queue)  */
-#define NAFB_XFLAG_QUEUE 19   /* push edition: next task of the queue                                          */
-                              /* [20..27] debug time stamps                                                    */
-#define NAFB_XFLAG_MAX_CHUNKS 16
-#define NAFB_XFLAG_CHUNK_TICKET 32 /* [32..47] push edition: finished push tasks per chunk                     */
-#define NAFB_XFLAG_PUSHED 64  /* [64 + 8 c + i] written by rank i: "chunk c of my gradient has landed in your staging area" */
-#define NAFB_XFLAG_WORDS 192
+#define NAFB_XFLAG_TICKET2 18 /* local block counter of the push edition's second phase                        */
+#define NAFB_XFLAG_WORDS 32
 
 typedef struct nafb_exchange {
     uint32_t world, rank;
@@ -338,9 +333,6 @@ typedef struct nafb_exchange {
                                           buffer of this rank (peers never read it; it leaves the kernel zeroed), grad_zero
                                           and grad[w != rank] are ignored.                                              */
     uint64_t stage_slot;               /* floats per staging slot, multiple of 4, >= the largest slice                  */
-    uint32_t push_chunks;              /* PUSH edition: chunks per slice the gradient push and the owners' Adam + parameter push
-                                          are pipelined over (0 = default 8, <= NAFB_XFLAG_MAX_CHUNKS); the same on every rank */
-    uint32_t reserved;
 } nafb_exchange;
 
 int nafb_peer_alloc(uint64_t bytes, void **ptr, unsigned char *handle64);

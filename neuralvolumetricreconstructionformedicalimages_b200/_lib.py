@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnafb200.so")
 DIAG_LIB_PATH = os.path.join(_HERE, "libnafb200_diag.so")   # diagnostics (tests / scripts only): include/nafb200_diag.h
 
-ABI_VERSION = 10
+ABI_VERSION = 9
 NAFB_MAX_LEVELS = 32
 NAFB_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
@@ -68,15 +68,14 @@ class Sampler(ctypes.Structure):
 
 NAFB_MAX_RANKS = 8
 STATE_STEP, STATE_SEED_LO, STATE_SEED_HI, STATE_TICKET, STATE_TICKET_FWD, STATE_LR, STATE_WORDS = 0, 1, 2, 4, 5, 6, 8   # LR: a double in words 6..7
-XFLAG_ARRIVE, XFLAG_DONE, XFLAG_ERROR, XFLAG_TICKET, XFLAG_TICKET2, XFLAG_QUEUE, XFLAG_CHUNK_TICKET, XFLAG_PUSHED, XFLAG_WORDS = 0, 8, 16, 17, 18, 19, 32, 64, 192
-XFLAG_MAX_CHUNKS = 16
+XFLAG_ARRIVE, XFLAG_DONE, XFLAG_ERROR, XFLAG_TICKET, XFLAG_TICKET2, XFLAG_WORDS = 0, 8, 16, 17, 18, 32
 
 
 class Exchange(ctypes.Structure):
     _fields_ = [("world", u32), ("rank", u32), ("param", ctypes.c_void_p * NAFB_MAX_RANKS), ("grad", ctypes.c_void_p * NAFB_MAX_RANKS),
                 ("flags", ctypes.c_void_p * NAFB_MAX_RANKS), ("grad_zero", ctypes.c_void_p), ("exp_avg", ctypes.c_void_p),
                 ("exp_avg_sq", ctypes.c_void_p), ("n", u64), ("state", ctypes.c_void_p), ("mc_param", ctypes.c_void_p),
-                ("mc_grad", ctypes.c_void_p), ("stage", ctypes.c_void_p * NAFB_MAX_RANKS), ("stage_slot", u64), ("push_chunks", u32), ("reserved", u32)]
+                ("mc_grad", ctypes.c_void_p), ("stage", ctypes.c_void_p * NAFB_MAX_RANKS), ("stage_slot", u64)]
 
 
 _SIGNATURES = {

@@ -48,8 +48,6 @@ struct ExchangeParams {
     float *stage[MAXR];    // push mode: every rank's staging area [W][slot4 float4] (slot r of rank w: written by rank r)
     float *grad_local;     // push mode: my (single) gradient buffer, cleared as it is consumed
     uint64_t slot4;        // float4 per staging slot (>= the largest slice)
-    uint32_t chunks, lag, np, no, total;   // push mode: chunks per slice, queue lag, push / own tasks per chunk, all tasks
-    uint64_t cap4;         // push mode: float4 per chunk (multiple of TASK4)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -210,34 +208,27 @@ __global__ void __launch_bounds__(512) k_adam_exchange(const ExchangeParams P) {
 
 // ---------------------------------------------------------------------------------------------------- push edition
 // NVLink carries posted WRITES at a higher rate than it serves READS (measured here: the pull kernel's remote loads reach
-// ~450 GB/s, its remote stores drain at ~570 GB/s), so this edition moves every byte with a store, and it PIPELINES the two
-// directions of the exchange chunk by chunk:
-//   push(c)  rank r copies chunk c of slice w of ITS gradient into slot r of rank w's staging area (remote stores), for every
-//            w != r, clearing what it has sent; when all of chunk c is globally visible it raises pushed[c][r] on every rank;
-//   own(c)   once pushed[c][*] have arrived, rank w adds the W contributions of chunk c of its slice in rank order (its own
-//            from the gradient buffer, the others from its local staging slots), applies Adam and stores the new parameters
-//            into all W replicas.
-// Both kinds of work are cut into tasks of TASK4 float4 that the (persistent, fully resident) blocks take from ONE queue
-// ordered   push(0) .. push(LAG-1), [push(c), own(c-LAG)] .., own(C-LAG) .. own(C-1):
-// a block that holds own(c) spins until the peers' chunk has landed while the others carry on with later pushes, so the
-// gradient traffic of chunk c+1.. and the parameter traffic of chunk c share the link's two directions, and the optimizer's HBM
-// traffic hides under both.  No deadlock: push tasks never wait, and every push(c) task has been handed out before the first
-// own(c' >= c) task is.  A pushed flag also says "r has left its backward pass": its parameters may be overwritten.
-// Peers never read a gradient buffer, so one gradient buffer per rank suffices and it leaves the kernel zeroed.
+// ~450 GB/s, its remote stores drain at ~570 GB/s, and the two phases hardly overlap), so this edition moves every byte with
+// a store:
+//   phase 1  rank r copies slice w of ITS gradient into slot r of rank w's staging area (remote stores), for every w != r,
+//            clearing its gradient as it goes; when all of that is globally visible it raises pushed[r] on every rank;
+//   phase 2  once pushed[*] have arrived, rank w adds the W contributions of its slice in rank order (its own from the
+//            gradient buffer, the others from its local staging slots), applies Adam and stores the new parameters into
+//            all W replicas; done[w] as before.
+// pushed[r] doubles as "r no longer reads its parameters".  Peers never read a gradient buffer, so one gradient buffer per
+// rank suffices (no parity) and it leaves the kernel zeroed.  Every block waits for flags that other GPUs raise only after
+// ALL their blocks have run phase 1, so the grid must be fully resident (the launcher sizes it from the occupancy).
 __device__ __forceinline__ void slice_of(uint64_t n4, uint32_t w, uint32_t world, uint64_t &a, uint64_t &b) {
     const uint64_t base = n4 / world, extra = n4 % world;
     a = w * base + (w < extra ? w : extra);
     b = a + base + (w < extra ? 1 : 0);
 }
 
-constexpr uint32_t TASK4 = 1024;   // float4 per task: 512 threads x 2
-
 template <int W>
 __global__ void __launch_bounds__(512) k_adam_exchange_push(const ExchangeParams P) {
     const uint32_t world = W > 0 ? (uint32_t)W : P.world;
     __shared__ AdamConst s_c;
-    __shared__ uint32_t s_epoch, s_last, s_task[3];
-    uint32_t *const lflags = P.flags[P.rank];
+    __shared__ uint32_t s_epoch, s_last;
     if (threadIdx.x == 0) {
         s_epoch = P.state ? P.state[NAFB_STATE_STEP] + 1u : P.epoch;
         s_c = P.state ? adam_const_from_state(P.state, P.beta1, P.beta2, P.eps, P.gscale) : P.c;
@@ -245,117 +236,73 @@ __global__ void __launch_bounds__(512) k_adam_exchange_push(const ExchangeParams
     __syncthreads();
     const uint32_t epoch = s_epoch;
     const AdamConst c = s_c;
-    unsigned long long *stamps = reinterpret_cast<unsigned long long *>(lflags + 20);   // debug: ns of %globaltimer
+    unsigned long long *stamps = reinterpret_cast<unsigned long long *>(P.flags[P.rank] + 20);   // debug: ns of block 0
     if (blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     float4 *g4 = reinterpret_cast<float4 *>(P.grad_local);
+
+    // ---- phase 1: push my contribution to every other owner, clearing what has been sent
+#pragma unroll 1
+    for (uint32_t k = 1; k < world; ++k) {
+        const uint32_t w = (P.rank + k) % world;          // start with my right neighbour: spreads the traffic over the links
+        uint64_t a, b;
+        slice_of(P.n4, w, world, a, b);
+        float4 *dst = reinterpret_cast<float4 *>(P.stage[w]) + (uint64_t)P.rank * P.slot4;
+        for (uint64_t i = a + gid; i < b; i += stride) {
+            const float4 v = g4[i];
+            st_peer(dst + (i - a), v);
+            g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(P.flags[P.rank] + NAFB_XFLAG_TICKET, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x == 0) P.flags[P.rank][NAFB_XFLAG_TICKET] = 0u;
+        if (threadIdx.x < world) st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_ARRIVE + P.rank, epoch);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = globaltimer_ns();
+    wait_all(P, NAFB_XFLAG_ARRIVE, epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[2] = globaltimer_ns();
+
+    // ---- phase 2: my slice
     float4 *m4 = reinterpret_cast<float4 *>(P.m), *v4 = reinterpret_cast<float4 *>(P.v);
     const float4 *p_in = reinterpret_cast<const float4 *>(P.param[P.rank]);
     const float4 *st = reinterpret_cast<const float4 *>(P.stage[P.rank]);
-    const uint32_t C = P.chunks, np = P.np, no = P.no;
-    const uint64_t my_len = P.s1 - P.s0;
-
-#pragma unroll 1
-    for (;;) {
-        // ---- next task of the queue: (kind, chunk, index)
-        if (threadIdx.x == 0) {
-            uint32_t t = atomicAdd(lflags + NAFB_XFLAG_QUEUE, 1u);
-            uint32_t kind = 2, chunk = 0;
-            if (t < P.total) {
-                for (uint32_t s = 0; s < C + P.lag; ++s) {
-                    const uint32_t n_push = s < C ? np : 0u, n_own = s >= P.lag ? no : 0u;
-                    if (t < n_push) { kind = 0; chunk = s; break; }
-                    t -= n_push;
-                    if (t < n_own) { kind = 1; chunk = s - P.lag; break; }
-                    t -= n_own;
-                }
-            }
-            s_task[0] = kind; s_task[1] = chunk; s_task[2] = t;
-        }
-        __syncthreads();
-        const uint32_t kind = s_task[0], chunk = s_task[1], idx = s_task[2];
-        __syncthreads();
-        if (kind == 2) break;
-        const uint64_t c0 = (uint64_t)chunk * P.cap4, c1 = c0 + P.cap4;
-        if (kind == 0) {
-            // ---- push: consecutive tasks go to different owners
-            const uint32_t k = 1u + idx % (world - 1u), sub = idx / (world - 1u);
-            const uint32_t w = (P.rank + k) % world;
-            uint64_t a, b;
-            slice_of(P.n4, w, world, a, b);
-            const uint64_t end = (b - a) < c1 ? (b - a) : c1;
-            float4 *dst = reinterpret_cast<float4 *>(P.stage[w]) + (uint64_t)P.rank * P.slot4;
-            const uint64_t o0 = c0 + (uint64_t)sub * TASK4 + threadIdx.x, o1 = o0 + 512;
-            float4 v0, v1;
-            if (o0 < end) v0 = g4[a + o0];
-            if (o1 < end) v1 = g4[a + o1];
-            if (o0 < end) { st_peer(dst + o0, v0); g4[a + o0] = make_float4(0.f, 0.f, 0.f, 0.f); }
-            if (o1 < end) { st_peer(dst + o1, v1); g4[a + o1] = make_float4(0.f, 0.f, 0.f, 0.f); }
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0 && atomicAdd(lflags + NAFB_XFLAG_CHUNK_TICKET + chunk, 1u) == np - 1u) {
-                lflags[NAFB_XFLAG_CHUNK_TICKET + chunk] = 0u;
-                __threadfence_system();
-                for (uint32_t r = 0; r < world; ++r) st_release_sys(P.flags[r] + NAFB_XFLAG_PUSHED + chunk * NAFB_MAX_RANKS + P.rank, epoch);
-                if (chunk == C - 1u) stamps[1] = globaltimer_ns();
-            }
-        } else {
-            // ---- own: wait for chunk `chunk` of every peer
-            if (threadIdx.x < world && threadIdx.x != P.rank) {
-                const uint32_t *f = lflags + NAFB_XFLAG_PUSHED + chunk * NAFB_MAX_RANKS + threadIdx.x;
-                const unsigned long long t0 = globaltimer_ns();
-                while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-                    if (globaltimer_ns() - t0 > TIMEOUT_NS) {
-                        atomicExch(lflags + NAFB_XFLAG_ERROR, 1u + NAFB_XFLAG_PUSHED + chunk * NAFB_MAX_RANKS + threadIdx.x);
-                        break;
-                    }
-                    __nanosleep(64);
-                }
-            }
-            __syncthreads();
-            const uint64_t end = my_len < c1 ? my_len : c1;
+    for (uint64_t i = P.s0 + gid; i < P.s1; i += stride) {
+        float4 g[MAXR];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const uint64_t o = c0 + (uint64_t)idx * TASK4 + (uint64_t)u * 512 + threadIdx.x;
-                if (o < end) {
-                    const uint64_t i = P.s0 + o;
-                    float4 g[MAXR];
+        for (int w = 0; w < MAXR; ++w)
+            if (w < (int)world) g[w] = (uint32_t)w == P.rank ? g4[i] : __ldcs(st + (uint64_t)w * P.slot4 + (i - P.s0));
+        float4 p = p_in[i], m = m4[i - P.s0], v = v4[i - P.s0];
+        float4 s = g[0];
 #pragma unroll
-                    for (int w = 0; w < MAXR; ++w)
-                        if (w < (int)world) g[w] = (uint32_t)w == P.rank ? g4[i] : __ldcg(st + (uint64_t)w * P.slot4 + o);
-                    float4 p = p_in[i], m = m4[o], v = v4[o];
-                    float4 s = g[0];
+        for (int w = 1; w < MAXR; ++w)
+            if (w < (int)world) { s.x += g[w].x; s.y += g[w].y; s.z += g[w].z; s.w += g[w].w; }
+        adam_one(p.x, s.x, m.x, v.x, c);
+        adam_one(p.y, s.y, m.y, v.y, c);
+        adam_one(p.z, s.z, m.z, v.z, c);
+        adam_one(p.w, s.w, m.w, v.w, c);
+        m4[i - P.s0] = m;
+        v4[i - P.s0] = v;
+        g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int w = 1; w < MAXR; ++w)
-                        if (w < (int)world) { s.x += g[w].x; s.y += g[w].y; s.z += g[w].z; s.w += g[w].w; }
-                    adam_one(p.x, s.x, m.x, v.x, c);
-                    adam_one(p.y, s.y, m.y, v.y, c);
-                    adam_one(p.z, s.z, m.z, v.z, c);
-                    adam_one(p.w, s.w, m.w, v.w, c);
-                    m4[o] = m;
-                    v4[o] = v;
-                    g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int w = 0; w < MAXR; ++w)
-                        if (w < (int)world) st_peer(reinterpret_cast<float4 *>(P.param[w]) + i, p);
-                }
-            }
-        }
+        for (int w = 0; w < MAXR; ++w)
+            if (w < (int)world) st_peer(reinterpret_cast<float4 *>(P.param[w]) + i, p);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamps[3] = globaltimer_ns();
     // ---- last block out: "done" to every rank, then wait until every rank is done with MY replica and MY staging area
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(lflags + NAFB_XFLAG_TICKET2, 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (threadIdx.x == 0) s_last = atomicAdd(P.flags[P.rank] + NAFB_XFLAG_TICKET2, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
     if (!s_last) return;
     __threadfence_system();
-    if (threadIdx.x == 0) {
-        lflags[NAFB_XFLAG_TICKET2] = 0u;
-        lflags[NAFB_XFLAG_QUEUE] = 0u;      // every block has taken its last (empty) ticket
-        stamps[2] = globaltimer_ns();
-    }
+    if (threadIdx.x == 0) P.flags[P.rank][NAFB_XFLAG_TICKET2] = 0u;
     if (threadIdx.x < world) st_release_sys(P.flags[threadIdx.x] + NAFB_XFLAG_DONE + P.rank, epoch);
     wait_all(P, NAFB_XFLAG_DONE, epoch);
-    if (threadIdx.x == 0) stamps[3] = globaltimer_ns();
     if (P.state && threadIdx.x == 0) P.state[NAFB_STATE_STEP] = epoch;
 }
 
@@ -448,15 +395,7 @@ int nafb_adam_exchange_step(const nafb_exchange *x, double lr, double beta1, dou
         }
         P.grad_local = x->grad[x->rank];
         P.slot4 = x->stage_slot >> 2;
-        const uint64_t max_len = (P.n4 + x->world - 1) / x->world;
-        if ((x->stage_slot & 3) || P.slot4 < max_len) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: stage_slot too small");
-        if (x->push_chunks > NAFB_XFLAG_MAX_CHUNKS) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: push_chunks %u > %d", x->push_chunks, NAFB_XFLAG_MAX_CHUNKS);
-        P.chunks = x->push_chunks ? x->push_chunks : 8u;
-        P.cap4 = ((max_len + P.chunks - 1) / P.chunks + TASK4 - 1) / TASK4 * TASK4;
-        P.lag = 1;
-        P.no = (uint32_t)(P.cap4 / TASK4);
-        P.np = (x->world - 1) * P.no;
-        P.total = P.chunks * (P.np + P.no);
+        if ((x->stage_slot & 3) || P.slot4 < (P.n4 + x->world - 1) / x->world) NAFB_FAIL(NAFB_ERR_INVALID, "adam_exchange_step: stage_slot too small");
     }
     // persistent grid: as many blocks of 512 threads as are resident at once (blocks spin on the arrival flags)
     cudaStream_t s = (cudaStream_t)stream;

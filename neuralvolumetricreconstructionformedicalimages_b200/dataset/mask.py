@@ -61,6 +61,7 @@ class PixelSampler:
         seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self.state = torch.from_numpy(np.array([0, seed & 0xFFFFFFFF, seed >> 32, 0], dtype=np.uint32).view(np.int32)).to(dev)
         self.order = None if order is None else torch.as_tensor(order, dtype=torch.int32, device=dev).contiguous()
+        self.version = 0      # bumped by every python-level call that moves the draw counter (NAFEngine's prefetch checks it)
         self._src = _lib.PixelSource(projs=self.projs.data_ptr(), mask=self.mask.data_ptr() if self.mask is not None else None,
                                      valid=self.valid_packed.data_ptr(), n_valid=self.n_valid.data_ptr(),
                                      order=self.order.data_ptr() if self.order is not None else None, n_proj=P, H=H, W=W,
@@ -70,15 +71,18 @@ class PixelSampler:
     def draw_into(self, n_rays: int, pixels: torch.Tensor, projs: torch.Tensor, mask: torch.Tensor | None):
         """Enqueue ONE draw (the next projection of the order) into caller-owned device buffers: pixels [N,3] int32, projs [N]
         fp32, mask [N] uint8 (or None).  Graph-capturable: the draw counter advances on the device."""
+        self.version += 1
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().nafb_draw_pixels(ctypes.byref(self._src), int(n_rays), _lib.ptr(pixels), _lib.ptr(projs), _lib.ptr(mask),
                                                    _lib.ptr(self.state), _lib.stream_ptr()))
 
     def set_draw(self, k: int):
         """Position of the draw counter (draw k takes projection order[k % len(order)])."""
+        self.version += 1
         self.state[0:1] = torch.tensor([int(k)], dtype=torch.int32)
 
     def draws_done(self) -> int:
+        """Draws made so far (synchronises).  NAFEngine.train_step_sampled keeps ONE draw ahead of the steps it has run."""
         return int(self.state[0].item())
 
     def check(self):
@@ -104,6 +108,7 @@ class PixelSampler:
         else:
             st = self.state.cpu().numpy().copy()
             self.state[0:1] += 1
+            self.version += 1
             st[0] = (int(st[0]) * 2654435761) & 0x7FFFFFFF     # decorrelate from draw_into's counter, keep the explicit projection below
         one = torch.tensor([proj], dtype=torch.int32, device=dev)
         state = torch.from_numpy(st).to(dev)

@@ -105,7 +105,7 @@ class PeerExchange:
               stores only over NVLink, one gradient buffer per rank (the default: fastest measured).
     """
 
-    FLAG_BYTES = 1024                  # >= 4 * _lib.XFLAG_WORDS; keeps the vectors behind it 256-byte aligned
+    FLAG_BYTES = 256
 
     def __init__(self, n, device, group, rank, world, backend="ipc"):
         """Set-up is COLLECTIVE and staged so that a failure on one rank never leaves the others inside a collective that
@@ -198,7 +198,6 @@ class PeerExchange:
                     x.stage[w] = base + stage_off
             if backend == "push":
                 x.stage_slot = slot
-                x.push_chunks = int(os.environ.get("NAFB_PUSH_CHUNKS", "0"))    # 0: the library's default (8); for sweeps
             else:
                 x.grad_zero = local_ptr + fb + (1 + (1 - par)) * seg
             x.exp_avg, x.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
@@ -312,6 +311,8 @@ class NAFEngine:
         self._init_state(seed)
         self._graphs = {}
         self._seen_batches = {}
+        self._prefetch = None        # (sampler, n_rays, buffers, sampler version) of the batch train_step_sampled has drawn ahead
+        self._side_stream = None
         self._eager_runs = {}
         self._host_seq = 0
         self._static = {}
@@ -630,7 +631,12 @@ class NAFEngine:
         src/dataset/tigre.py:354-382 + train.py:59-60,93-95): the draw kernel writes the pixels, projection values and mask bits of
         the next projection straight into the buffers the fused step reads, and the whole iteration -- draw, forward + loss,
         backward, optimizer -- is ONE CUDA graph with no per-step host input at all (needs set_geometry).  Returns the loss as a
-        0-dim device tensor."""
+        0-dim device tensor.
+
+        The draw of step k+1 is made by step k, on a second stream beside the optimizer kernel (the draw is one latency-bound
+        CTA): the sampler is therefore ONE draw ahead of the steps run (`sampler.draws_done() == steps + 1`); the sequence of
+        batches is exactly that of `draw_into` + `train_step(pixels=...)`.  If anything else moves the sampler between two steps
+        (set_draw, draw, draw_into) the prefetched batch is discarded and the step draws afresh."""
         if getattr(self, "poses", None) is None:
             raise RuntimeError("train_step_sampled needs NAFEngine.set_geometry(angles, geo) first")
         N, with_mask = int(n_rays), sampler.mask is not None
@@ -638,10 +644,24 @@ class NAFEngine:
         with torch.cuda.device(self.device):
             par = self._parity()
             in_graph = not (self.world_size > 1 and self.px is None)
+            # the step's batch: normally already there -- the previous step drew it while its optimizer ran (below).  Otherwise
+            # (first step, another n_rays, or somebody else moved the sampler: set_draw / draw / draw_into) draw it now.
+            if self._prefetch != (id(sampler), N, id(s), sampler.version):
+                sampler.draw_into(N, s["pixels"], s["projs"], s["mask"])
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            side = self._side_stream
 
             def body(with_optimizer):
-                sampler.draw_into(N, s["pixels"], s["projs"], s["mask"])
-                self._whole_step(s, par, None, None, with_optimizer=with_optimizer, use_pixels=True)
+                self._whole_step(s, par, None, None, with_optimizer=False, use_pixels=True)
+                # fork: the NEXT step's draw (one CTA, ~40 us of latency-bound work that needs nothing but the sampler's device
+                # state) runs beside the optimizer; forward and backward have consumed this step's batch
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    sampler.draw_into(N, s["pixels"], s["projs"], s["mask"])
+                if with_optimizer:
+                    self._finish_step(par)
+                torch.cuda.current_stream(self.device).wait_stream(side)
 
             key = (N, with_mask, par, "sampled", id(sampler))
             g = self._graphs.get(key)
@@ -657,6 +677,7 @@ class NAFEngine:
                 g.replay()
                 if not in_graph:
                     self._finish_step(par)
+            self._prefetch = (id(sampler), N, id(s), sampler.version)
             self.step_count += 1
         return s["loss"][0]
 

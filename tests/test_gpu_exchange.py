@@ -33,11 +33,11 @@ def test_exchange_kernel_world1_bit_exact_vs_adam():
     L_ = _lib.lib()
     n = 4 * 25_003          # not a multiple of the block size
     g = torch.Generator(device=DEV).manual_seed(5)
-    buf = _lib.peer_alloc(1024 + 3 * n * 4)
+    buf = _lib.peer_alloc(256 + 3 * n * 4)
     flags = buf.tensor(0, _lib.XFLAG_WORDS, torch.int32, DEV)
-    param = buf.tensor(1024, n, torch.float32, DEV)
-    grad0 = buf.tensor(1024 + n * 4, n, torch.float32, DEV)
-    grad1 = buf.tensor(1024 + 2 * n * 4, n, torch.float32, DEV)
+    param = buf.tensor(256, n, torch.float32, DEV)
+    grad0 = buf.tensor(256 + n * 4, n, torch.float32, DEV)
+    grad1 = buf.tensor(256 + 2 * n * 4, n, torch.float32, DEV)
     param.copy_(torch.randn(n, device=DEV, generator=g))
     grad0.copy_(torch.randn(n, device=DEV, generator=g) * 1e-2)
     grad1.fill_(7.0)                                        # stale other-parity buffer: must come back zeroed
@@ -46,8 +46,8 @@ def test_exchange_kernel_world1_bit_exact_vs_adam():
     ref = [param.clone(), grad0.clone(), m.clone(), v.clone()]
     x = _lib.Exchange()
     x.world, x.rank, x.n = 1, 0, n
-    x.flags[0], x.param[0], x.grad[0] = buf.ptr, buf.ptr + 1024, buf.ptr + 1024 + n * 4
-    x.grad_zero = buf.ptr + 1024 + 2 * n * 4
+    x.flags[0], x.param[0], x.grad[0] = buf.ptr, buf.ptr + 256, buf.ptr + 256 + n * 4
+    x.grad_zero = buf.ptr + 256 + 2 * n * 4
     x.exp_avg, x.exp_avg_sq = m.data_ptr(), v.data_ptr()
     for step in (1, 2, 9):
         _lib.check(L_.nafb_adam_exchange_step(ctypes.byref(x), 1e-3, 0.9, 0.999, 1e-8, step, 1.0, _lib.stream_ptr()))
@@ -59,26 +59,23 @@ def test_exchange_kernel_world1_bit_exact_vs_adam():
         assert int(grad1.abs().max().item()) == 0
         f = flags.cpu().numpy()
         assert f[_lib.XFLAG_ARRIVE] == step and f[_lib.XFLAG_DONE] == step and f[_lib.XFLAG_ERROR] == 0 and f[_lib.XFLAG_TICKET] == 0
-    # ---- push edition, world 1: no peers to push to, the owner's chunk tasks alone must reproduce the dense kernel
+    # ---- push edition, world 1: no peers to push to, the owner phase alone must reproduce the dense kernel
     stage = torch.zeros(n, device=DEV)
     x.stage[0], x.stage_slot, x.grad_zero = stage.data_ptr(), n, None
-    for step, chunks in ((10, 0), (11, 1), (12, 3), (13, 16)):
+    for step in (10, 11):
         grad0.copy_(torch.randn(n, device=DEV, generator=g) * 1e-2)
         ref[1].copy_(grad0)
-        x.push_chunks = chunks
         _lib.check(L_.nafb_adam_exchange_step(ctypes.byref(x), 1e-3, 0.9, 0.999, 1e-8, step, 1.0, _lib.stream_ptr()))
         _lib.check(L_.nafb_adam_step(_lib.ptr(ref[0]), _lib.ptr(ref[1]), _lib.ptr(ref[2]), _lib.ptr(ref[3]), n, 1e-3, 0.9, 0.999, 1e-8, step,
                                      1.0, 1, _lib.stream_ptr()))
         torch.cuda.synchronize()
-        assert torch.equal(param, ref[0]) and torch.equal(m, ref[2]) and torch.equal(v, ref[3]), chunks
+        assert torch.equal(param, ref[0]) and torch.equal(m, ref[2]) and torch.equal(v, ref[3])
         assert int(grad0.abs().max().item()) == 0           # the push edition's single gradient buffer leaves the kernel zeroed
         f = flags.cpu().numpy()
-        assert f[_lib.XFLAG_DONE] == step and f[_lib.XFLAG_ERROR] == 0 and f[_lib.XFLAG_TICKET2] == 0 and f[_lib.XFLAG_QUEUE] == 0
-        assert not f[_lib.XFLAG_CHUNK_TICKET:_lib.XFLAG_CHUNK_TICKET + _lib.XFLAG_MAX_CHUNKS].any()
-    x.push_chunks = 17
-    with pytest.raises(RuntimeError):
-        _lib.check(L_.nafb_adam_exchange_step(ctypes.byref(x), 1e-3, 0.9, 0.999, 1e-8, 14, 1.0, _lib.stream_ptr()))
-    x.push_chunks = 0
+        assert f[_lib.XFLAG_DONE] == step and f[_lib.XFLAG_ERROR] == 0 and f[_lib.XFLAG_TICKET] == 0 and f[_lib.XFLAG_TICKET2] == 0
+    x.stage_slot = n // 2 // 4 * 4
+    with pytest.raises(RuntimeError):                       # staging slot smaller than the slice
+        _lib.check(L_.nafb_adam_exchange_step(ctypes.byref(x), 1e-3, 0.9, 0.999, 1e-8, 12, 1.0, _lib.stream_ptr()))
     i0, i1 = _lib.exchange_slice(n, 0, 1)
     assert (i0, i1) == (0, n)
     spans = [_lib.exchange_slice(n, r, 8) for r in range(8)]

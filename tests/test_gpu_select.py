@@ -180,7 +180,16 @@ def test_train_step_sampled_equals_draw_then_train_step():
         assert bool((pix[:, 0] == k % 5).all()) and 0 < int(msk.sum()) < N
         l2 = float(e2.train_step(None, val.clone(), msk.clone(), pixels=pix.clone()))
         np.testing.assert_allclose(l1, l2, rtol=1e-5)
-    assert s1.draws_done() == 7 and e1.step_count == 7
+    assert s1.draws_done() == 8 and e1.step_count == 7          # one draw ahead: step k draws the batch of step k + 1 beside its optimizer
+    # somebody else moves the sampler: the prefetched batch is dropped, the next step draws afresh -- here draw 3 again, on both sides
+    s1.set_draw(3)
+    s2.set_draw(3)
+    l1 = float(e1.train_step_sampled(s1, N))
+    s2.draw_into(N, pix, val, msk)
+    assert bool((pix[:, 0] == 3).all())
+    l2 = float(e2.train_step(None, val.clone(), msk.clone(), pixels=pix.clone()))
+    np.testing.assert_allclose(l1, l2, rtol=1e-5)
+    assert s1.draws_done() == 5
     s1.check()
     e1.check_health()
     assert float((e1.flat_param - e2.flat_param).abs().max()) < 5e-5
