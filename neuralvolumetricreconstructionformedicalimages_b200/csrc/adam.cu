@@ -94,12 +94,7 @@ extern "C" int nafb_adam_step_dev(float *param, float *grad, float *exp_avg, flo
         NAFB_FAIL(NAFB_ERR_INVALID, "adam_step_dev: buffers must be 16-byte aligned");
     if (n == 0 || (n & 3)) NAFB_FAIL(NAFB_ERR_INVALID, "adam_step_dev: n must be a positive multiple of 4");
     uint64_t blocks = ((n >> 2) + 255) / 256;
-    static int per_sm = 0;   // experiment knob: NAFB_ADAM_BLOCKS_PER_SM (default 8 = every thread slot of the SM)
-    if (per_sm == 0) {
-        const char *e = getenv("NAFB_ADAM_BLOCKS_PER_SM");
-        per_sm = e && atoi(e) > 0 ? atoi(e) : 8;
-    }
-    const uint64_t cap = (uint64_t)nafb_sm_count() * per_sm;
+    const uint64_t cap = (uint64_t)nafb_sm_count() * 8;   // two waves of the 4 blocks per SM the registers allow (4 or 6 measured slower)
     if (blocks > cap) blocks = cap;
     k_adam_dev<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, grad_scale, zero_grad, state);
     NAFB_CHECK_LAUNCH("adam_step_dev");

@@ -649,7 +649,9 @@ class NAFEngine:
             if self._prefetch != (id(sampler), N, id(s), sampler.version):
                 sampler.draw_into(N, s["pixels"], s["projs"], s["mask"])
             if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream(device=self.device)
+                # high priority: when the backward pass retires, the draw's single CTA must get its SM before the optimizer's
+                # persistent blocks fill every thread slot (it would otherwise run after them)
+                self._side_stream = torch.cuda.Stream(device=self.device, priority=-1)
             side = self._side_stream
 
             def body(with_optimizer):
