@@ -20,5 +20,5 @@ for i in range(30):
         s = raw[20:28].view(np.uint64).astype(np.int64)
         rows.append([(s[1] - s[0]) / 1e3, (s[2] - s[1]) / 1e3, (s[3] - s[2]) / 1e3, (s[3] - s[0]) / 1e3])
 r = np.array(rows)
-print(f"rank {rank} mode {eng.exchange_mode}: stamps d01 {r[:,0].mean():.1f} us, d12 {r[:,1].mean():.1f} us, d23 {r[:,2].mean():.1f} us, total {r[:,3].mean():.1f} us (pull: wait-arrive / zero+slice / tail+done; push: start -> last chunk pushed / -> queue empty / -> peers done)", flush=True)
+print(f"rank {rank} mode {eng.exchange_mode}: stamps d01 {r[:,0].mean():.1f} us, d12 {r[:,1].mean():.1f} us, d23 {r[:,2].mean():.1f} us, total {r[:,3].mean():.1f} us (pull: wait-arrive / zero+slice / tail+done; push: push / wait-pushed / slice)", flush=True)
 dist.barrier(); dist.destroy_process_group()
