@@ -241,17 +241,35 @@ __global__ void __launch_bounds__(512) k_adam_exchange_push(const ExchangeParams
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     float4 *g4 = reinterpret_cast<float4 *>(P.grad_local);
 
-    // ---- phase 1: push my contribution to every other owner, clearing what has been sent
+    // ---- phase 1: push my contribution to every other owner, clearing what has been sent.  Work items = (piece of blockDim
+    // float4, owner) with the owner varying fastest, so at every moment the grid's stores are spread evenly over all W - 1
+    // destinations whatever the skew between the ranks (a schedule "everybody sends to rank + k" is a permutation only while the
+    // ranks stay in lockstep).  Measured at 8 GPUs: the same 0.404 ms/step either way -- the all-to-all push of 50 MB per GPU
+    // takes ~125 us (400 GB/s per GPU; a single pair reaches 665 GB/s) however it is ordered.
+    if (world > 1) {
+        const uint64_t max_len = (P.n4 + world - 1) / world, pieces = (max_len + blockDim.x - 1) / blockDim.x;
+        const uint64_t items = pieces * (world - 1u);
 #pragma unroll 1
-    for (uint32_t k = 1; k < world; ++k) {
-        const uint32_t w = (P.rank + k) % world;          // start with my right neighbour: spreads the traffic over the links
-        uint64_t a, b;
-        slice_of(P.n4, w, world, a, b);
-        float4 *dst = reinterpret_cast<float4 *>(P.stage[w]) + (uint64_t)P.rank * P.slot4;
-        for (uint64_t i = a + gid; i < b; i += stride) {
-            const float4 v = g4[i];
-            st_peer(dst + (i - a), v);
-            g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint64_t id0 = blockIdx.x; id0 < items; id0 += 2ull * gridDim.x) {
+            float4 v[2];
+            float4 *src[2], *dst[2];
+            bool ok[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint64_t id = id0 + (uint64_t)u * gridDim.x;
+                const uint32_t k = 1u + (uint32_t)(id % (world - 1u));
+                const uint32_t w = (P.rank + k) % world;
+                uint64_t a, b;
+                slice_of(P.n4, w, world, a, b);
+                const uint64_t off = (id / (world - 1u)) * blockDim.x + threadIdx.x;
+                ok[u] = id < items && a + off < b;
+                src[u] = g4 + a + off;
+                dst[u] = reinterpret_cast<float4 *>(P.stage[w]) + (uint64_t)P.rank * P.slot4 + off;
+                if (ok[u]) v[u] = *src[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (ok[u]) { st_peer(dst[u], v[u]); *src[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
         }
     }
     __threadfence_system();
