@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAFB_ABI_VERSION 9
+#define NAFB_ABI_VERSION 10
 
 enum nafb_status { NAFB_OK = 0, NAFB_ERR_INVALID = 1, NAFB_ERR_UNSUPPORTED = 2, NAFB_ERR_CUDA = 3 };
 /* head activation of the density MLP: reference src/network/network.py:23-32 */
@@ -223,6 +223,18 @@ int nafb_density_backward(const nafb_grid *grid, const nafb_mlp *mlp, const nafb
  * sum_i |pts[r,i+1]-pts[r,i]|_1 per ray (render.py:16-28) when non-NULL. */
 int nafb_sample_points(const nafb_sampler *smp, float *z_vals, float *pts, float *tv_partial,
                        nafb_stream_t stream);
+
+/* Hierarchical ("fine") sampling of a ray batch in one kernel (render.py:113-126 with sample_pdf :215-247): per ray the
+ * piecewise-constant pdf of the coarse weights[1:-1] (+ 1e-5) over the midpoints of z_vals is inverted at n_fine uniforms
+ * (searchsorted right=True, denominators below 1e-5 replaced by 1), the new depths are merged with the coarse ones (sorted
+ * ascending) and the clamped sample positions of all S + n_fine depths are written.
+ *   rays [N,8], z_vals [N,S] ascending, weights [N,S]; u [N,u_stride >= n_fine] uniforms in [0,1) -- or u_stride == 0: one row
+ *   [n_fine] shared by all rays (the reference's deterministic linspace(0,1,n_fine) when perturb == 0);
+ *   z_out [N,S+n_fine], pts_out [N,S+n_fine,3], tv_partial [N] = sum_i |pts[i+1]-pts[i]|_1 (render.py:16-28); any output may be NULL.
+ * n_samples >= 3, n_samples + n_fine <= 1024 (NAFB_ERR_UNSUPPORTED otherwise). */
+int nafb_sample_fine(const float *rays, const float *z_vals, const float *weights, const float *u, uint32_t u_stride,
+                     uint32_t n_rays, uint32_t n_samples, uint32_t n_fine, float clamp, float *z_out, float *pts_out,
+                     float *tv_partial, nafb_stream_t stream);
 /* rays_out [N,8] for the detector pixels of the sampler (the in-kernel generator written out). */
 int nafb_generate_rays(const nafb_sampler *smp, float *rays_out, nafb_stream_t stream);
 /* raw2outputs (render.py:178-212), raw [N,S,out_dim] (channel 0 integrated): acc [N];

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnafb200.so")
 DIAG_LIB_PATH = os.path.join(_HERE, "libnafb200_diag.so")   # diagnostics (tests / scripts only): include/nafb200_diag.h
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 NAFB_MAX_LEVELS = 32
 NAFB_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
@@ -101,6 +101,7 @@ _SIGNATURES = {
     "nafb_density_backward_workspace_bytes": (u64, [ctypes.POINTER(Mlp)]),
     "nafb_density_backward": (ctypes.c_int, [ctypes.POINTER(Grid), ctypes.POINTER(Mlp), ctypes.POINTER(Sampler), ctypes.c_int, c_f32p, c_f32p, ctypes.POINTER(MlpGrads), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nafb_sample_points": (ctypes.c_int, [ctypes.POINTER(Sampler), c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
+    "nafb_sample_fine": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, u32, u32, u32, u32, ctypes.c_float, c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
     "nafb_generate_rays": (ctypes.c_int, [ctypes.POINTER(Sampler), c_f32p, ctypes.c_void_p]),
     "nafb_ray_integral_forward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),
     "nafb_ray_integral_backward": (ctypes.c_int, [c_f32p, u32, c_f32p, c_f32p, c_f32p, u32, u32, ctypes.c_void_p]),

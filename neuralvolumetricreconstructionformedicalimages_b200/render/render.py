@@ -20,6 +20,9 @@ from ..network.network import DensityNetwork
 # The reference prints a warning when an output contains NaN/Inf (render.py:141-144), which costs
 # several host synchronisations per chunk.  Opt in with CHECK_NUMERICS = True.
 CHECK_NUMERICS = False
+# Hierarchical sampling (n_fine > 0): sample_pdf + merge + sort + positions + TV as one kernel (nafb_sample_fine).  False: the
+# same stages as torch operators (kept for A/B tests and for shapes the kernel does not take).
+FUSED_FINE_SAMPLING = True
 
 
 def compute_tv_regularization(pts):
@@ -152,6 +155,31 @@ def sample_pdf(bins, weights, N_samples, det=False):
     return bin_lo + t * (bin_hi - bin_lo)
 
 
+def sample_fine(rays, z_vals, weights, n_fine, det, bound, want_tv=True):
+    """The fine pass's sampling stage as ONE kernel (render.py:113-126): sample_pdf over the midpoints of z_vals with
+    weights[..., 1:-1], merge + sort with the coarse depths, clamped sample positions, per-ray TV partial sums.
+    The uniforms are drawn exactly as the reference draws them (torch.rand on the CPU generator, or linspace when det)."""
+    import numpy as np
+    L_ = _lib.lib()
+    rays = _lib.require_cuda(rays.contiguous(), "rays")
+    z_vals = _lib.require_cuda(z_vals.contiguous(), "z_vals")
+    weights = _lib.require_cuda(weights.detach().contiguous(), "weights")
+    N, S = z_vals.shape
+    dev = rays.device
+    if det:
+        u, u_stride = torch.linspace(0., 1., steps=n_fine).to(dev), 0                    # render.py:228-229
+    else:
+        u, u_stride = torch.rand([N, n_fine]).contiguous().to(dev), n_fine               # render.py:230-233 (CPU generator)
+    M = S + n_fine
+    z = torch.empty(N, M, device=dev, dtype=torch.float32)
+    pts = torch.empty(N, M, 3, device=dev, dtype=torch.float32)
+    tv = torch.empty(N, device=dev, dtype=torch.float32) if want_tv else None
+    with torch.cuda.device(dev):
+        _lib.check(L_.nafb_sample_fine(_lib.ptr(rays), _lib.ptr(z_vals), _lib.ptr(weights), _lib.ptr(u), u_stride, N, S, int(n_fine),
+                                       float(np.float32(bound - 1e-6)), _lib.ptr(z), _lib.ptr(pts), _lib.ptr(tv), _lib.stream_ptr()))
+    return z, pts, tv
+
+
 def render(rays, net, net_fine, n_samples, n_fine, perturb, netchunk, raw_noise_std, chunk_size=None):
     """Render projections for ``rays`` [N, 8] (origin, direction, near, far).
 
@@ -187,14 +215,18 @@ def render_chunk(rays, net, net_fine, n_samples, n_fine, perturb, netchunk, raw_
         ret = {}
         if use_fine:
             ret.update(acc0=acc, weights0=weights, pts0=pts)
-            z_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
-            z_samples = sample_pdf(z_mid, weights[..., 1:-1], n_fine, det=(perturb == 0.)).detach()
-            z_vals, _ = torch.sort(torch.cat([z_vals, z_samples], -1), -1)
-            bound = net.bound - 1e-6
-            pts = (rays[..., None, :3] + rays[..., None, 3:6] * z_vals[..., :, None]).clamp(-bound, bound)
+            if FUSED_FINE_SAMPLING and rays.dtype == torch.float32 and 3 <= n_samples and n_samples + n_fine <= 1024:
+                z_vals, pts, tv = sample_fine(rays, z_vals, weights, n_fine, perturb == 0., net.bound)   # one kernel
+                tv_loss = tv.sum() * 0.1
+            else:
+                z_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+                z_samples = sample_pdf(z_mid, weights[..., 1:-1], n_fine, det=(perturb == 0.)).detach()
+                z_vals, _ = torch.sort(torch.cat([z_vals, z_samples], -1), -1)
+                bound = net.bound - 1e-6
+                pts = (rays[..., None, :3] + rays[..., None, 3:6] * z_vals[..., :, None]).clamp(-bound, bound)
+                tv_loss = compute_tv_regularization(pts) * 0.1
             raw = run_network(pts, net_fine, netchunk)
             acc, _ = raw2outputs(raw, z_vals, rays[..., 3:6], raw_noise_std)
-            tv_loss = compute_tv_regularization(pts) * 0.1
         else:
             tv_loss = tv.sum() * 0.1
         ret.update(acc=acc, pts=pts, tv_loss=tv_loss)

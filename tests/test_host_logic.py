@@ -115,7 +115,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == _lib.exported_symbols()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.nafb_abi_version() == 9
+    assert L.nafb_abi_version() == 10
     # the diagnostics library exports what include/nafb200_diag.h declares, and the product library does not carry them
     dh = open(os.path.join(ROOT, "include", "nafb200_diag.h")).read()
     D = _lib.diag_lib()
