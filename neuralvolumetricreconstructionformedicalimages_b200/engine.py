@@ -646,7 +646,8 @@ class NAFEngine:
             in_graph = not (self.world_size > 1 and self.px is None)
             # the step's batch: normally already there -- the previous step drew it while its optimizer ran (below).  Otherwise
             # (first step, another n_rays, or somebody else moved the sampler: set_draw / draw / draw_into) draw it now.
-            if self._prefetch != (id(sampler), N, id(s), sampler.version):
+            pf = self._prefetch
+            if not (pf is not None and pf[0] is sampler and pf[1] == N and pf[2] is s and pf[3] == sampler.version):
                 sampler.draw_into(N, s["pixels"], s["projs"], s["mask"])
             if self._side_stream is None:
                 # high priority: when the backward pass retires, the draw's single CTA must get its SM before the optimizer's
@@ -679,7 +680,7 @@ class NAFEngine:
                 g.replay()
                 if not in_graph:
                     self._finish_step(par)
-            self._prefetch = (id(sampler), N, id(s), sampler.version)
+            self._prefetch = (sampler, N, s, sampler.version)     # the objects themselves: an id() could be recycled
             self.step_count += 1
         return s["loss"][0]
 
