@@ -455,7 +455,7 @@ def extra_workloads(device, world, rank):
                                                    "applicable limit is the address-divergent load rate of the L1TEX / L2 path: see `limiter`",
                                            "limiter": {"bound": "l1tex_gather", "achieved_gops_upper_bound": 128 * vox_per_rank / (vq_ms * 1e-3) / 1e9,
                                                        "peak_gops": L2_GATHER_GOPS,
-                                                       "note": "128 corner loads per voxel before x-neighbour pair merging and L1 hits (a 4x4x8 block of "
+                                                       "note": "128 corner loads per voxel before x-neighbour pair merging and L1 hits (an 8x4x4 block of "
                                                                "the lattice per tile shares sectors); the random-access micro-benchmark is not a ceiling "
                                                                "for spatially coherent points"}}}
     del eng, vol

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128 * NQ, NQ == 2 ? 3 : 2) k_density_fwd_tc(co
         uint64_t p = tile * TILE + r;      // index of the point in the outputs
         bool valid = p < P;
         float x[3] = {0.f, 0.f, 0.f};
-        if constexpr (SRC == NAFB_SRC_VOXELS) valid = voxel_block_point(sp, tile, (uint32_t)r, x, p);   // 4 x 4 x 8 blocks of the lattice
+        if constexpr (SRC == NAFB_SRC_VOXELS) valid = voxel_block_point(sp, tile, (uint32_t)r, x, p);   // 8 x 4 x 4 blocks of the lattice
         float z_mine = 0.f, delta_mine = 0.f;   // RAYS source: this sample's depth and its ray-integral weight delta_i |d|
         uint32_t ray_mine = 0xffffffffu;
         if constexpr (SRC == NAFB_SRC_RAYS) {
@@ -363,7 +363,7 @@ int launch_fwd_tc_n(const GridParams &gp, const nafb_mlp &mp, const SamplerParam
                     int32_t *flags, uint8_t *stash, const nafb_loss_tail &tail, cudaStream_t s) {
     static bool configured[NAFB_MAX_DEVICES] = {};
     NAFB_CONFIGURE_SMEM(configured, (k_density_fwd_tc<SRC, C, NQ>), (int)FWD_SMEM, "density_forward(tc)");
-    const uint64_t n_tiles = SRC == NAFB_SRC_VOXELS ? (uint64_t)((sp.i1 - sp.i0 + 3) / 4) * ((sp.n2 + 3) / 4) * ((sp.n3 + 7) / 8) : (P + TILE - 1) / TILE;
+    const uint64_t n_tiles = SRC == NAFB_SRC_VOXELS ? voxel_block_tiles(sp) : (P + TILE - 1) / TILE;
     const uint64_t cap = (uint64_t)nafb_sm_count() * (NQ == 2 ? 3 : 2);
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
     const int dbg = nafb_debug_flags();
