@@ -1,7 +1,7 @@
 # fine-sampling kernel: its tests, the A/B against the reference's render, then the whole GPU suite
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_fine.py -m gpu -q -x > gpurun_out/r2d_fine.log 2>&1; echo "fine rc $?"; grep -E "passed|failed|FAILED|^E  " gpurun_out/r2d_fine.log | tail -12
+timeout 600 python -m pytest tests/test_gpu_fine_and_guard.py -m gpu -q -x > gpurun_out/r2d_fine.log 2>&1; echo "fine rc $?"; grep -E "passed|failed|FAILED|^E  " gpurun_out/r2d_fine.log | tail -12
 python - <<'PY'
 import torch, time, importlib
 R = importlib.import_module('neuralvolumetricreconstructionformedicalimages_b200.render.render')

@@ -108,3 +108,37 @@ def test_render_fine_pass_kernel_vs_operator_path():
         assert float((d > 1e-5).float().mean()) < 0.01            # a sample next to a bin edge may hop; everything else agrees
         np.testing.assert_allclose(a["acc"].detach().cpu().numpy(), b["acc"].detach().cpu().numpy(), rtol=2e-4, atol=1e-7)
         np.testing.assert_allclose(float(a["tv_loss"]), float(b["tv_loss"]), rtol=1e-4)
+
+
+def test_numerics_guard_positive_cases():
+    """The guard the reference runs after every render chunk (render.py:141-144: `torch.isnan / isinf` on the outputs) and the range
+    check of hashgrid.py:122 are ONE flag word OR-ed by the fused kernel: bit 0 = a position outside [-bound, bound], bit 1 = a
+    non-finite activation.  The negative case (flags == 0) is asserted by the parity tests; here both bits must RISE, in the
+    tensor-core and in the fp32 SIMT arithmetic, and the drop-in modules must turn them into the reference's behaviour."""
+    from neuralvolumetricreconstructionformedicalimages_b200 import _lib, fused
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder import get_encoder
+    from neuralvolumetricreconstructionformedicalimages_b200.network import get_network
+    torch.manual_seed(0)
+    enc = get_encoder("hashgrid", input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19)
+    net = get_network("mlp")(enc, bound=0.3, num_layers=4, hidden_dim=32, skips=[2], out_dim=1, last_activation="sigmoid").to(DEV)
+    meta = net.fused_meta()
+    pts = (torch.rand(1000, 3, device=DEV) - 0.5) * 0.58
+    for arith in (_lib.ARITH_TC, _lib.ARITH_SIMT):
+        meta.arith = arith
+        flags = torch.zeros(1, dtype=torch.int32, device=DEV)
+        fused.density_forward(meta, net.encoder.embeddings.detach(), [p.detach() for p in net.flat_params()], pts=pts, flags=flags)
+        assert int(flags.item()) == 0
+        bad = pts.clone()
+        bad[137, 1] = 0.31                                       # outside the [-0.3, 0.3] box
+        fused.density_forward(meta, net.encoder.embeddings.detach(), [p.detach() for p in net.flat_params()], pts=bad, flags=flags)
+        assert int(flags.item()) == 1
+        flags.zero_()
+        table = net.encoder.embeddings.detach().clone()
+        table[: 17 ** 3] = float("nan")                          # level 0 (dense, 17^3 entries): every point reads it
+        out = fused.density_forward(meta, table, [p.detach() for p in net.flat_params()], pts=pts, flags=flags)
+        assert int(flags.item()) == 2 and bool(torch.isnan(out["sigma"]).any())
+    # the module raises what the reference's encoder raises (hashgrid.py:122-123)
+    bad = pts.clone()
+    bad[5, 0] = -0.4
+    with pytest.raises(ValueError, match="not in"):
+        net(bad)
