@@ -68,13 +68,20 @@ constexpr int AGG_LEVELS = 8;      // levels 0 .. AGG_LEVELS-1 may be aggregated
 constexpr int AGG_MAX_RUNS = 20;   // aggregate when the warp has at most this many runs
 // (both can be overridden for experiments through NAFB_DEBUG_SKIP: bits 8-13 = levels + 1, bits 16-21 = runs + 1)
 
-template <int C>
-__device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, const int l, const float x0, const float x1, const float x2,
-                                         const uint32_t taddr, const bool valid, const int agg_max_runs, float *__restrict__ grad_table) {
+// One level of the scatter for the point this lane holds.  The level's gradient `ge` comes either from TMEM (`taddr`, the fused
+// backward kernel: the load is issued first and awaited after the index arithmetic) or from registers (`ge_in`, the native-op
+// backward of hashgrid.cu).  All 32 lanes of the warp must call it (shuffles); `valid` masks lanes without a point.
+template <int C, bool FROM_TMEM>
+__device__ __forceinline__ void scatter_level(const LevelParams lp, const float x0, const float x1, const float x2, const uint32_t taddr,
+                                              const float *ge_in, const bool valid, const int agg_max_runs, float *__restrict__ grad_table) {
     const unsigned lane = threadIdx.x & 31u;
     float ge[C];
-    umma::tmem_ldn<C>(taddr, ge);
-    const LevelParams lp = lvs[l];
+    if constexpr (FROM_TMEM) {
+        umma::tmem_ldn<C>(taddr, ge);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) ge[c] = ge_in[c];
+    }
     float *tab = grad_table + (size_t)lp.offset * C;
     const uint32_t par = addr_parity8(tab);
     uint32_t g[3];
@@ -85,7 +92,7 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
     const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
     uint32_t e[8];
     cell_entries8(lp, ct, e);
-    umma::tmem_wait_ld();
+    if constexpr (FROM_TMEM) umma::tmem_wait_ld();
     if (agg_max_runs > 0) {
         // runs of equal cells among consecutive lanes (invalid lanes: a run of their own, never issued)
         const uint32_t k0 = valid ? (g[0] | (g[1] << 16)) : 0xffffffffu, k1 = valid ? g[2] : 0xffffffffu;
@@ -137,6 +144,14 @@ __device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, co
             red_add_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v0, v1);
         }
     }
+}
+
+// the fused backward kernel's entry: one __noinline__ copy serves all levels (the fully unrolled version spent 17 % of its samples in
+// instruction-cache misses)
+template <int C>
+__device__ __noinline__ void scatter_one(const LevelParams *__restrict__ lvs, const int l, const float x0, const float x1, const float x2,
+                                         const uint32_t taddr, const bool valid, const int agg_max_runs, float *__restrict__ grad_table) {
+    scatter_level<C, true>(lvs[l], x0, x1, x2, taddr, nullptr, valid, agg_max_runs, grad_table);
 }
 
 // Backward pass without a stash: gather the thread's 16 encoding columns level by level (rolled loop, one copy of

@@ -4,6 +4,7 @@
 // table entries are fetched with one vector load per corner (float2 for C=2) on the read-only
 // path, gradients leave with one vector `red.global.add` per corner.
 #include "common.cuh"
+#include "density_tc.cuh"   // pair-merged loads / reductions and the warp-aggregated scatter shared with the fused kernels
 
 namespace {
 
@@ -35,8 +36,17 @@ __device__ __forceinline__ void encode_level(const GridParams &gp, uint32_t leve
 #pragma unroll
     for (int d = 0; d < D; ++d) locate(x01[d], lp.scale, g[d], f[d]);
     float v[1 << D][C];
+    if constexpr (D == 3) {   // hoisted index terms; the two x-neighbours of a (y, z) corner share one 128-bit load when adjacent + aligned
+        const uint32_t par = addr_parity8(tab);
+        const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
+        uint32_t e[8];
+        cell_entries8(lp, ct, e);
 #pragma unroll
-    for (uint32_t idx = 0; idx < (1u << D); ++idx) load_entry<C>(tab, corner_entry<D>(lp, g, idx), v[idx]);
+        for (uint32_t j = 0; j < 4; ++j) load_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[2 * j], v[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) load_entry<C>(tab, corner_entry<D>(lp, g, idx), v[idx]);
+    }
 #pragma unroll
     for (int c = 0; c < C; ++c) res[c] = 0.f;
 #pragma unroll
@@ -121,33 +131,48 @@ __global__ void __launch_bounds__(256) k_hash_fwd_blc(GridParams gp, const float
     }
 }
 
-// ---- backward scatter: thread = (point, level); grad is [B, L*C] (BLC) or [L,B,C] (LBC)
+// ---- backward scatter: thread = (point, level); grad is [B, L*C] (BLC) or [L,B,C] (LBC).  D == 3: the scatter of the fused
+// backward kernel (density_tc.cuh scatter_level): x-neighbour pairs leave as one red.v4 when adjacent + aligned, and on the coarse
+// levels the lanes of a warp (32 consecutive points: consecutive samples of a ray in render()'s order) that fall into one cell are
+// summed by shuffles and reduced once.
 template <int D, int C>
 __global__ void __launch_bounds__(256) k_hash_bwd(GridParams gp, const float *__restrict__ grad, const float *__restrict__ inputs,
                                                    float *__restrict__ grad_table, uint32_t B, int layout) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const bool valid = b < B;
+    if constexpr (D != 3) {
+        if (!valid) return;
+    }
     const uint32_t level = blockIdx.y;
     const LevelParams lp = gp.lv[level];
     float x[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) x[d] = __ldg(inputs + (size_t)b * D + d);
-    const float *gptr = layout == NAFB_LAYOUT_BLC ? grad + ((size_t)b * gp.L + level) * C : grad + ((size_t)level * B + b) * C;
     float gr[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) gr[c] = __ldg(gptr + c);
-    uint32_t g[D];
-    float f[D];
+    for (int d = 0; d < D; ++d) x[d] = valid ? __ldg(inputs + (size_t)b * D + d) : 0.f;
+    if (valid) {
+        const float *gptr = layout == NAFB_LAYOUT_BLC ? grad + ((size_t)b * gp.L + level) * C : grad + ((size_t)level * B + b) * C;
 #pragma unroll
-    for (int d = 0; d < D; ++d) locate(x[d], lp.scale, g[d], f[d]);
-    float *tab = grad_table + (size_t)lp.offset * C;
+        for (int c = 0; c < C; ++c) gr[c] = __ldg(gptr + c);
+    } else {
 #pragma unroll
-    for (uint32_t idx = 0; idx < (1u << D); ++idx) {
-        const float w = corner_weight<D>(f, idx);
-        float v[C];
+        for (int c = 0; c < C; ++c) gr[c] = 0.f;
+    }
+    if constexpr (D == 3) {
+        tc::scatter_level<C, false>(lp, x[0], x[1], x[2], 0u, gr, valid, (int)level < tc::AGG_LEVELS ? tc::AGG_MAX_RUNS : 0, grad_table);
+    } else {
+        uint32_t g[D];
+        float f[D];
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = __fmul_rn(w, gr[c]);  // hashencoder.cu:268
-        red_add_entry<C>(tab, corner_entry<D>(lp, g, idx), v);
+        for (int d = 0; d < D; ++d) locate(x[d], lp.scale, g[d], f[d]);
+        float *tab = grad_table + (size_t)lp.offset * C;
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+            const float w = corner_weight<D>(f, idx);
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __fmul_rn(w, gr[c]);  // hashencoder.cu:268
+            red_add_entry<C>(tab, corner_entry<D>(lp, g, idx), v);
+        }
     }
 }
 
