@@ -131,6 +131,71 @@ __global__ void __launch_bounds__(256) k_hash_fwd_blc(GridParams gp, const float
     }
 }
 
+// ---- forward, [B, L*C] layout, D == 3, no dy_dx: thread = POINT, levels in a loop with the loads of the next level in flight
+// while one is interpolated (the gather of the fused forward kernel).  The lanes of a warp are 32 consecutive points working on
+// the SAME level, so on the coarse levels they hit the same lines (with thread = (point, level) and the level fastest, every lane of
+// a warp reads another level's table); each thread writes its point's whole 128-byte row.  Same loads, same operation order:
+// bit-identical to k_hash_fwd_blc.
+template <int C>
+__global__ void __launch_bounds__(256) k_hash_fwd_point(GridParams gp, const float *__restrict__ inputs, float *__restrict__ outputs, uint32_t B) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float x[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = __ldg(inputs + (size_t)b * 3 + d);
+    float *o = outputs + (size_t)b * gp.L * C;
+    float v[2][8][C];
+    auto issue = [&](const uint32_t l, const int slot) {
+        const LevelParams lp = gp.lv[l];
+        const float *__restrict__ tab = gp.table + (size_t)lp.offset * C;
+        uint32_t g[3];
+        float f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) locate(x[d], lp.scale, g[d], f[d]);
+        const uint32_t par = addr_parity8(tab);
+        const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
+        uint32_t e[8];
+        cell_entries8(lp, ct, e);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) load_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[slot][2 * j], v[slot][2 * j + 1]);
+    };
+    auto consume = [&](const uint32_t l, const int slot, float (&res)[C]) {
+        uint32_t g;
+        float f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) locate(x[d], gp.lv[l].scale, g, f[d]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) res[c] = 0.f;
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            const float w = corner_weight<3>(f, idx);
+#pragma unroll
+            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[slot][idx][c], res[c]);  // hashencoder.cu:139
+        }
+    };
+    issue(0, 0);
+    for (uint32_t l = 0; l < gp.L; l += 2) {
+        float r0[C], r1[C];
+        if (l + 1 < gp.L) issue(l + 1, 1);
+        consume(l, 0, r0);
+        if (l + 2 < gp.L) issue(l + 2, 0);
+        if (l + 1 < gp.L) {
+            consume(l + 1, 1, r1);
+            if constexpr (C == 2) {
+                if ((gp.L & 1u) == 0u) {   // rows are 16-byte aligned: one 128-bit store per level pair
+                    *reinterpret_cast<float4 *>(o + (size_t)l * 2) = make_float4(r0[0], r0[1], r1[0], r1[1]);
+                    continue;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) { o[(size_t)l * C + c] = r0[c]; o[(size_t)(l + 1) * C + c] = r1[c]; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) o[(size_t)l * C + c] = r0[c];
+        }
+    }
+}
+
 // ---- backward scatter: thread = (point, level); grad is [B, L*C] (BLC) or [L,B,C] (LBC).  D == 3: the scatter of the fused
 // backward kernel (density_tc.cuh scatter_level): x-neighbour pairs leave as one red.v4 when adjacent + aligned, and on the coarse
 // levels the lanes of a warp (32 consecutive points: consecutive samples of a ray in render()'s order) that fall into one cell are
@@ -232,6 +297,8 @@ int launch_fwd(const GridParams &gp, const float *inputs, float *outputs, uint32
     if (layout == NAFB_LAYOUT_LBC) {
         dim3 grid((B + 255) / 256, gp.L);
         k_hash_fwd_lbc<D, C><<<grid, 256, 0, s>>>(gp, inputs, outputs, B, dy_dx);
+    } else if (D == 3 && !dy_dx && ((uintptr_t)outputs & 15) == 0) {
+        if constexpr (D == 3) k_hash_fwd_point<C><<<(B + 255) / 256, 256, 0, s>>>(gp, inputs, outputs, B);
     } else {
         const uint64_t n = (uint64_t)B * gp.L;
         k_hash_fwd_blc<D, C><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gp, inputs, outputs, B, dy_dx);

@@ -15,6 +15,23 @@ from torch.autograd import Function
 from .. import _lib
 
 
+_OFFSETS_CACHE = {}
+
+
+def _offsets_host(offsets: torch.Tensor) -> np.ndarray:
+    """The level offsets as a host int32 array.  The reference's op receives them as a device tensor (hashgrid.py:28); reading
+    them back costs a device-to-host copy + a stream synchronisation, so the copy is made once per tensor VERSION."""
+    key = (offsets.data_ptr(), offsets._version, offsets.numel(), str(offsets.device))
+    hit = _OFFSETS_CACHE.get(key)
+    if hit is None:
+        if len(_OFFSETS_CACHE) > 64:
+            _OFFSETS_CACHE.clear()
+        hit = np.ascontiguousarray(offsets.detach().cpu().numpy(), dtype=np.int32)
+        hit.setflags(write=False)
+        _OFFSETS_CACHE[key] = hit
+    return hit
+
+
 class _hash_encode(Function):
     """Same contract as the reference autograd.Function (hashgrid.py:10-71):
     inputs [B, D] in [0, 1], embeddings [sO, C], offsets [L+1] int32 -> [B, L*C].
@@ -30,7 +47,7 @@ class _hash_encode(Function):
         _lib.require_floating(embeddings, "embeddings", like=inputs)
         if offsets.dtype != torch.int32:
             raise RuntimeError("offsets must be an int tensor")
-        offsets_np = np.ascontiguousarray(offsets.detach().cpu().numpy(), dtype=np.int32)
+        offsets_np = _offsets_host(offsets)
         B, D = inputs.shape
         L = offsets_np.shape[0] - 1
         C = embeddings.shape[1]

@@ -47,6 +47,16 @@ def measure(enc, name):
         enc(pts, 0.3).backward(g)
     both = timeit(fb)
     print(f"{name}: forward {fwd:.1f} us, forward + backward {both:.1f} us (backward ~ {both - fwd:.1f} us) for {pts.shape[0]} points", flush=True)
+    # kernel-only times of the op itself (the module adds the range check with its host synchronisation and the normalisation)
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(10):
+            fb()
+        torch.cuda.synchronize()
+    rows = [(e.key, e.count, getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0.0)) for e in prof.key_averages()]
+    ker = [(k, c, t / max(c, 1)) for k, c, t in rows if "hash" in k.lower() or "kernel_grid" in k.lower()]
+    import re
+    print("    kernels: " + "; ".join(f"{(re.search(r'(k_hash\w+|kernel_grid\w*)', k) or [k])[0]} {t:.1f} us" for k, c, t in ker), flush=True)
     enc.embeddings.grad = None
     out = enc(pts, 0.3)
     out.backward(g)
