@@ -136,6 +136,69 @@ __global__ void __launch_bounds__(256) k_hash_fwd_blc(GridParams gp, const float
 // the SAME level, so on the coarse levels they hit the same lines (with thread = (point, level) and the level fastest, every lane of
 // a warp reads another level's table); each thread writes its point's whole 128-byte row.  Same loads, same operation order:
 // bit-identical to k_hash_fwd_blc.
+// The same for the shape every shipped configuration has (16 levels x 2 features: rows of 128 bytes): the outputs are staged in
+// shared memory and every warp writes its 32 rows with whole-line stores (56 us against 63 us with one 16-byte store per level
+// pair and thread, chest_50 point set).  DEPTH = levels of loads in flight ahead of the one being interpolated: 1, 2 and 3 measure
+// the same (56-57 us; 4 and 8 cost occupancy: 70 us) -- the gather runs at 0.76 of the L2's random-sector rate whatever the depth
+// (scripts/native_fwd_time.py, scripts/calls/r2_call48.sh).
+template <int C, int DEPTH>
+__global__ void __launch_bounds__(256) k_hash_fwd_point16(GridParams gp, const float *__restrict__ inputs, float *__restrict__ outputs, uint32_t B) {
+    constexpr int LMAX = 16, ROW = LMAX * C + 4;
+    __shared__ __align__(16) float stage[256 * ROW];
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    float x[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = b < B ? __ldg(inputs + (size_t)b * 3 + d) : 0.5f;
+    float v[LMAX][8][C];
+    auto issue = [&](const int l) {
+        const LevelParams lp = gp.lv[l];
+        const float *__restrict__ tab = gp.table + (size_t)lp.offset * C;
+        uint32_t g[3];
+        float f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) locate(x[d], lp.scale, g[d], f[d]);
+        const uint32_t par = addr_parity8(tab);
+        const CellTerms ct = cell_terms3(lp, g[0], g[1], g[2]);
+        uint32_t e[8];
+        cell_entries8(lp, ct, e);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) load_entry_pair<C>(tab, par, e[2 * j], e[2 * j + 1], v[l][2 * j], v[l][2 * j + 1]);
+    };
+#pragma unroll
+    for (int l = 0; l < DEPTH; ++l) issue(l);
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+        if (l + DEPTH < LMAX) issue(l + DEPTH);
+        uint32_t g;
+        float f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) locate(x[d], gp.lv[l].scale, g, f[d]);
+        float res[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) res[c] = 0.f;
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            const float w = corner_weight<3>(f, idx);
+#pragma unroll
+            for (int c = 0; c < C; ++c) res[c] = __fmaf_rn(w, v[l][idx][c], res[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) stage[(threadIdx.x) * ROW + l * C + c] = res[c];
+    }
+    // each warp writes its 32 rows (128 B each for L*C = 32) with whole-line stores: 8 lanes x 16 B per row, 4 rows per instruction
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31u, w0 = threadIdx.x & ~31u;
+    const uint32_t b0 = blockIdx.x * blockDim.x + w0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const uint32_t row = it * 4 + (lane >> 3), col4 = lane & 7u;
+        if (b0 + row < B) {
+            const float4 q = *reinterpret_cast<const float4 *>(&stage[(w0 + row) * ROW + col4 * 4]);
+            *reinterpret_cast<float4 *>(outputs + (size_t)(b0 + row) * (LMAX * C) + col4 * 4) = q;
+        }
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(256) k_hash_fwd_point(GridParams gp, const float *__restrict__ inputs, float *__restrict__ outputs, uint32_t B) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,7 +361,14 @@ int launch_fwd(const GridParams &gp, const float *inputs, float *outputs, uint32
         dim3 grid((B + 255) / 256, gp.L);
         k_hash_fwd_lbc<D, C><<<grid, 256, 0, s>>>(gp, inputs, outputs, B, dy_dx);
     } else if (D == 3 && !dy_dx && ((uintptr_t)outputs & 15) == 0) {
-        if constexpr (D == 3) k_hash_fwd_point<C><<<(B + 255) / 256, 256, 0, s>>>(gp, inputs, outputs, B);
+        if constexpr (D == 3) {
+            if constexpr (C == 2) {
+                if (gp.L == 16) k_hash_fwd_point16<2, 1><<<(B + 255) / 256, 256, 0, s>>>(gp, inputs, outputs, B);
+                else k_hash_fwd_point<C><<<(B + 255) / 256, 256, 0, s>>>(gp, inputs, outputs, B);
+            } else {
+                k_hash_fwd_point<C><<<(B + 255) / 256, 256, 0, s>>>(gp, inputs, outputs, B);
+            }
+        }
     } else {
         const uint64_t n = (uint64_t)B * gp.L;
         k_hash_fwd_blc<D, C><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gp, inputs, outputs, B, dy_dx);
@@ -310,6 +380,8 @@ int launch_fwd(const GridParams &gp, const float *inputs, float *outputs, uint32
 template <int D, int C>
 int launch_bwd(const GridParams &gp, const float *grad, const float *inputs, float *grad_table, uint32_t B, int layout,
                const float *dy_dx, float *grad_inputs, cudaStream_t s) {
+    // thread = (point, level), level = blockIdx.y.  (A thread-per-point version with the levels looped, like the forward kernel, is
+    // slower here: 104 us against 93 us -- the reductions want the sixteen-fold parallelism.)
     dim3 grid((B + 255) / 256, gp.L);
     k_hash_bwd<D, C><<<grid, 256, 0, s>>>(gp, grad, inputs, grad_table, B, layout);
     NAFB_CHECK_LAUNCH("hash_encode_backward");
