@@ -286,3 +286,16 @@ def test_host_staging_and_pending_loss_logic():
     assert not p2.done()
     flag[0] = 41
     assert p2.done() and p2.result() == 0.5 and ev2.synced == 0
+
+
+def test_level_offsets_are_read_back_once_per_tensor_version():
+    """encoder/hashgrid.py::_offsets_host: the op receives the level offsets as a tensor (reference hashgrid.py:28); the host copy the
+    C ABI needs is cached per (storage, version), and an in-place change of the tensor invalidates it."""
+    from neuralvolumetricreconstructionformedicalimages_b200.encoder import hashgrid as HG
+    offs = torch.tensor([0, 10, 30, 70], dtype=torch.int32)
+    a = HG._offsets_host(offs)
+    assert a.dtype == np.int32 and a.tolist() == [0, 10, 30, 70] and not a.flags.writeable
+    assert HG._offsets_host(offs) is a
+    offs[3] = 90
+    b = HG._offsets_host(offs)
+    assert b is not a and b.tolist() == [0, 10, 30, 90]
