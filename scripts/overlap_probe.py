@@ -40,4 +40,4 @@ def both():
     sA.wait_stream(cur); sB.wait_stream(cur)
     adam(sA); fwd(sB)
     cur.wait_stream(sA); cur.wait_stream(sB)
-print("blocks/SM", os.environ.get("NAFB_ADAM_BLOCKS_PER_SM", "8"), "adam alone %.1f us, fwd alone %.1f us, concurrent %.1f us" % (timeit(lambda: adam(cur)), timeit(lambda: fwd(cur)), timeit(both)))
+print("adam alone %.1f us, fwd alone %.1f us, concurrent %.1f us" % (timeit(lambda: adam(cur)), timeit(lambda: fwd(cur)), timeit(both)))
