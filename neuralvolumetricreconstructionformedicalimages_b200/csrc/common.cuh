@@ -182,8 +182,9 @@ template <int C>
 __device__ __forceinline__ void load_entry_pair(const float *__restrict__ tab, uint32_t par, uint32_t e0, uint32_t e1, float (&v0)[C],
                                                 float (&v1)[C]) {
     if constexpr (C == 2) {
-        const uint32_t lo = e0 < e1 ? e0 : e1, hi = e0 < e1 ? e1 : e0;
-        if (hi - lo == 1u && ((lo + par) & 1u) == 0u) {
+        // adjacent AND aligned <=> the two indices, shifted by the level's parity, differ in bit 0 only
+        if (((e0 + par) ^ (e1 + par)) == 1u) {
+            const uint32_t lo = e0 < e1 ? e0 : e1;
             const float4 q = __ldg(reinterpret_cast<const float4 *>(tab + 2 * (size_t)lo));
             const bool fwd = e0 < e1;
             v0[0] = fwd ? q.x : q.z; v0[1] = fwd ? q.y : q.w;
@@ -199,8 +200,8 @@ template <int C>
 __device__ __forceinline__ void red_add_entry_pair(float *tab, uint32_t par, uint32_t e0, uint32_t e1, const float (&v0)[C],
                                                    const float (&v1)[C]) {
     if constexpr (C == 2) {
-        const uint32_t lo = e0 < e1 ? e0 : e1, hi = e0 < e1 ? e1 : e0;
-        if (hi - lo == 1u && ((lo + par) & 1u) == 0u) {
+        if (((e0 + par) ^ (e1 + par)) == 1u) {
+            const uint32_t lo = e0 < e1 ? e0 : e1;
             const bool fwd = e0 < e1;
             red_add_f32x4(tab + 2 * (size_t)lo, fwd ? v0[0] : v1[0], fwd ? v0[1] : v1[1], fwd ? v1[0] : v0[0], fwd ? v1[1] : v0[1]);
             return;
@@ -230,7 +231,8 @@ __device__ __forceinline__ void st_l2hint(float4 *a, const float4 v, uint64_t po
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
 
-__device__ __forceinline__ float leaky_relu(float x) { return x > 0.f ? x : 0.01f * x; }
+// x > 0 ? x : 0.01 x, as max(x, 0.01 x): the same value for every input (0.01 x > x exactly when x < 0), one instruction less
+__device__ __forceinline__ float leaky_relu(float x) { return fmaxf(x, __fmul_rn(0.01f, x)); }
 
 __device__ __forceinline__ float head_activation(float x, uint32_t head) {
     switch (head) {

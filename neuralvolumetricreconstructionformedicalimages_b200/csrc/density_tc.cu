@@ -157,7 +157,12 @@ __global__ void __launch_bounds__(128 * NQ, NQ == 2 ? 3 : 2) k_density_fwd_tc(co
             // the rays of this tile (two when n_samples >= 128) are generated / loaded ONCE into shared memory; every thread then
             // places its own sample from there (no global loads, no dependent chain pixels -> poses per thread)
             const uint64_t p_first = tile * TILE, p_last = (p_first + TILE - 1 < P ? p_first + TILE - 1 : P - 1);
-            const uint32_t ray_first = (uint32_t)(p_first / sp.n_samples), ray_last = (uint32_t)(p_last / sp.n_samples);
+            uint32_t ray_first, ray_last;
+            if (P <= 0xffffffffull) {   // 32-bit divisions (a 64-bit one costs ~80 instructions, twice per thread and tile)
+                ray_first = (uint32_t)p_first / sp.n_samples; ray_last = (uint32_t)p_last / sp.n_samples;
+            } else {
+                ray_first = (uint32_t)(p_first / sp.n_samples); ray_last = (uint32_t)(p_last / sp.n_samples);
+            }
             const bool in_smem = ray_last - ray_first < (uint32_t)TILE_RAYS;
             if (in_smem) {
                 if (t <= (int)(ray_last - ray_first)) {
