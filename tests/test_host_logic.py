@@ -299,3 +299,25 @@ def test_level_offsets_are_read_back_once_per_tensor_version():
     offs[3] = 90
     b = HG._offsets_host(offs)
     assert b is not a and b.tolist() == [0, 10, 30, 90]
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """ABI drift guard: every struct of include/nafb200.h has the size -- and its last field the offset -- that the ctypes mirror in
+    _lib.py assumes (a C program compiled against the header prints them)."""
+    import subprocess
+    from neuralvolumetricreconstructionformedicalimages_b200 import _lib
+    pairs = [("nafb_grid", _lib.Grid), ("nafb_mlp", _lib.Mlp), ("nafb_mlp_grads", _lib.MlpGrads), ("nafb_sampler", _lib.Sampler),
+             ("nafb_loss_tail", _lib.LossTail), ("nafb_pixel_source", _lib.PixelSource), ("nafb_exchange", _lib.Exchange)]
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "nafb200.h"', "int main(void) {"]
+    for cname, ct in pairs:
+        last = ct._fields_[-1][0]
+        src.append(f'  printf("{cname} %zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));')
+    src += ['  printf("abi %d\\n", NAFB_ABI_VERSION);', "  return 0;", "}"]
+    c_file, exe = tmp_path / "abi_sizes.c", tmp_path / "abi_sizes"
+    c_file.write_text("\n".join(src))
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(c_file), "-o", str(exe)], check=True)
+    out = dict((l.split()[0], [int(v) for v in l.split()[1:]]) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert out["abi"] == [_lib.ABI_VERSION]
+    for cname, ct in pairs:
+        last = ct._fields_[-1][0]
+        assert out[cname] == [ctypes.sizeof(ct), getattr(ct, last).offset], (cname, out[cname], ctypes.sizeof(ct), getattr(ct, last).offset)
